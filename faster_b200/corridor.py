@@ -1,0 +1,100 @@
+"""Synthetic corridor problems shaped like the inputs Faster::replan() feeds SolverGurobi.
+
+Input generator for tests and bench.py only (JPS3D and the ellipsoid decomposition stay host-side input
+generators); the conventions follow SURVEY.md Appendix B:
+  * one polytope per polyline segment (jps_manager.cpp:113), rows A x <= b with outward unit normals,
+    sign-normalised w.r.t. the segment midpoint (polyhedron.h:131-152);
+  * face order: obstacle-derived half-spaces (inflated by drone_radius, line_segment.h:178-190), then the six
+    local-bbox faces +-dir_h (half width 2), +dir beyond p2 / -dir behind p1 (2), +-dir_v (1)
+    (line_segment.h:57-98, jps_manager.cpp:100), then the ground face -z <= -z_ground (jps_manager.cpp:118-122);
+  * whole: x0 = committed plan state, xf = rest at the last vertex (faster.cpp:402-407);
+    safe: same model with forceFinalConstraint=false (faster.cpp:521-524).
+"""
+import itertools
+import numpy as np
+
+UAV = dict(lim=(5.0, 5.0, 8.0), z_ground=0.0, drone_radius=0.42, bbox=(2.0, 2.0, 1.0), seg=(1.0, 1.5),
+           z=(0.5, 1.5), turn=60.0, v0=(0.0, 2.0))           # faster.yaml:7,14,18,23-25,39
+GROUND = dict(lim=(1.4, 1.4, 5.0), z_ground=-0.2, drone_radius=0.5, bbox=(2.0, 0.8, 0.4), seg=(0.5, 0.9),
+              z=(0.2, 0.2), turn=45.0, v0=(0.0, 0.8))        # Readme.md:112-124
+
+
+def monotone_sigmas(N, P):
+    """All non-decreasing interval->polytope assignments: C(N+P-1, P-1) rows of length N (uint8)."""
+    out = []
+    for cuts in itertools.combinations_with_replacement(range(N + 1), P - 1):
+        s = np.zeros(N, np.uint8)
+        for c in cuts:
+            s[c:] += 1
+        out.append(s)
+    return np.array(sorted(map(tuple, out)), np.uint8).reshape(-1, N)
+
+
+def sample_monotone_sigmas(N, P, n, rng):
+    """n distinct-ish monotone assignments for large (N,P) where the full list is too long."""
+    cuts = np.sort(rng.integers(0, N + 1, size=(n, P - 1)), axis=1)
+    s = np.zeros((n, N), np.uint8)
+    for k in range(P - 1):
+        s += (np.arange(N)[None, :] >= cuts[:, k:k + 1]).astype(np.uint8)
+    return s
+
+
+def _segment_polytope(p1, p2, rng, prof, n_cut):
+    d = p2 - p1
+    dirv = d / np.linalg.norm(d)
+    dir_h = np.array([dirv[1], -dirv[0], 0.0])
+    if np.linalg.norm(dir_h) == 0:
+        dir_h = np.array([-1.0, 0.0, 0.0])
+    dir_h /= np.linalg.norm(dir_h)
+    dir_v = np.cross(dirv, dir_h)
+    planes = []                                              # (point, outward normal)
+    r = prof["drone_radius"]
+    for _ in range(n_cut):
+        s = rng.uniform(0.0, 1.0)
+        c = p1 + s * d
+        ang = rng.uniform(0, 2 * np.pi)
+        n = np.cos(ang) * dir_h + np.sin(ang) * dir_v + rng.uniform(-0.3, 0.3) * dirv
+        n /= np.linalg.norm(n)
+        dist = rng.uniform(r + 0.12, r + 1.2)                # obstacle point at c + dist*n, inflated by r
+        planes.append((c + (dist - r) * n, n))
+    bb = prof["bbox"]
+    planes += [(p1 + dir_h * bb[1], dir_h), (p1 - dir_h * bb[1], -dir_h),
+               (p2 + dirv * bb[0], dirv), (p1 - dirv * bb[0], -dirv),
+               (p1 + dir_v * bb[2], dir_v), (p1 - dir_v * bb[2], -dir_v)]
+    mid = 0.5 * (p1 + p2)
+    A, b = [], []
+    for pt, n in planes:
+        c = float(pt @ n)
+        if n @ mid - c > 0:
+            n, c = -n, -c
+        A.append(n)
+        b.append(c)
+    A.append(np.array([0.0, 0.0, -1.0]))
+    b.append(-prof["z_ground"])
+    return np.array(A), np.array(b)
+
+
+def make_corridor(seed, P, N, profile="uav", force_final=True, DC=0.01):
+    """One corridor problem: dict(N, P, x0[9], xf[9], lim[3], polys[(A,b)], force_final, DC, verts)."""
+    prof = UAV if profile == "uav" else GROUND
+    rng = np.random.default_rng(seed)
+    verts = [np.array([rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(*prof["z"])])]
+    yaw = rng.uniform(-np.pi, np.pi)
+    for _ in range(P):
+        yaw += np.deg2rad(rng.uniform(-prof["turn"], prof["turn"]))
+        L = rng.uniform(*prof["seg"])
+        z = rng.uniform(*prof["z"])
+        nxt = verts[-1] + np.array([L * np.cos(yaw), L * np.sin(yaw), 0.0])
+        nxt[2] = z
+        verts.append(nxt)
+    polys = [_segment_polytope(verts[i], verts[i + 1], rng, prof, int(rng.integers(1, 7))) for i in range(P)]
+    d0 = verts[1] - verts[0]
+    d0 /= np.linalg.norm(d0)
+    x0 = np.zeros(9)
+    x0[:3] = verts[0]
+    x0[3:6] = d0 * rng.uniform(*prof["v0"])
+    x0[6:9] = rng.uniform(-0.3, 0.3, 3) * (0.0 if profile != "uav" else 1.0)
+    xf = np.zeros(9)
+    xf[:3] = verts[-1]
+    return dict(N=N, P=P, x0=x0, xf=xf, lim=np.array(prof["lim"]), polys=polys, force_final=bool(force_final),
+                DC=DC, verts=np.array(verts), seed=seed, profile=profile)

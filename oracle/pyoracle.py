@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes loader for oracle/_build/libfq_oracle.so (the CPU restatement).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libfq_oracle.so")
+_lib = None
+
+_d = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "fq_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.fqo_dt_initial.restype = C.c_double
+        L.fqo_dt_initial.argtypes = [_d, _d, _d, C.c_int]
+        L.fqo_num_samples.restype = C.c_int
+        L.fqo_num_samples.argtypes = [C.c_int, C.c_double, C.c_double]
+        L.fqo_fill_x.restype = None
+        L.fqo_fill_x.argtypes = [C.c_int, _d, C.c_double, C.c_double, C.c_int, _d]
+        _lib = L
+    return _lib
+
+
+def pack_polys(polys):
+    """list of (A[F,3], b[F]) -> (P, face_ofs int32[P+1], Ab float64[SF,4])."""
+    ofs = [0]
+    rows = []
+    for A, b in polys:
+        A = np.asarray(A, float).reshape(-1, 3)
+        b = np.asarray(b, float).reshape(-1)
+        rows.append(np.hstack([A, b[:, None]]))
+        ofs.append(ofs[-1] + A.shape[0])
+    Ab = np.ascontiguousarray(np.vstack(rows) if rows else np.zeros((0, 4)), dtype=np.float64)
+    if Ab.shape[0] == 0:
+        Ab = np.zeros((1, 4))
+    return len(polys), np.asarray(ofs, np.int32), Ab
+
+
+def _a(x, n):
+    x = np.ascontiguousarray(np.asarray(x, np.float64).reshape(-1))
+    assert x.size == n
+    return x
+
+
+def solve_fixed(N, x0, xf, lim, dt, polys, sigma, force_final=True):
+    """-> (status, cost, coeffs[N,12], iters); status 1 optimal, 0 infeasible, -1 numeric."""
+    L = lib()
+    P, ofs, Ab = pack_polys(polys)
+    sig = np.ascontiguousarray(np.asarray(sigma if sigma is not None else np.zeros(N), np.uint8))
+    cost = C.c_double(np.inf)
+    it = C.c_int(0)
+    co = np.zeros(12 * N)
+    rc = L.fqo_solve_fixed(C.c_int(N), C.c_int(int(force_final)), _a(x0, 9).ctypes, _a(xf, 9).ctypes,
+                           _a(lim, 3).ctypes, C.c_int(P), ofs.ctypes, Ab.ctypes, C.c_double(dt), sig.ctypes,
+                           C.byref(cost), co.ctypes, C.byref(it))
+    return rc, cost.value, co.reshape(N, 12), it.value
+
+
+def solve_batch(N, x0, xf, lim, polys, dts, sigmas, force_final=True, want_coeffs=False, threads=1):
+    L = lib()
+    P, ofs, Ab = pack_polys(polys)
+    dts = np.ascontiguousarray(dts, np.float64)
+    n = dts.size
+    sig = np.ascontiguousarray(np.asarray(sigmas, np.uint8).reshape(n, N))
+    feas = np.zeros(n, np.uint8)
+    cost = np.zeros(n)
+    co = np.zeros((n, N, 12)) if want_coeffs else None
+    L.fqo_solve_batch(C.c_int(N), C.c_int(int(force_final)), _a(x0, 9).ctypes, _a(xf, 9).ctypes, _a(lim, 3).ctypes,
+                      C.c_int(P), ofs.ctypes, Ab.ctypes, C.c_int(n), dts.ctypes, sig.ctypes, feas.ctypes,
+                      cost.ctypes, co.ctypes if want_coeffs else None, C.c_int(threads))
+    return feas, cost, co
+
+
+def solve_miqp(N, x0, xf, lim, dt, polys, force_final=True):
+    """Branch and bound over ALL sigma in P^N -> (status, cost, coeffs, sigma, nodes)."""
+    L = lib()
+    P, ofs, Ab = pack_polys(polys)
+    sig = np.zeros(N, np.uint8)
+    cost = C.c_double(np.inf)
+    nodes = C.c_long(0)
+    co = np.zeros(12 * N)
+    rc = L.fqo_solve_miqp(C.c_int(N), C.c_int(int(force_final)), _a(x0, 9).ctypes, _a(xf, 9).ctypes,
+                          _a(lim, 3).ctypes, C.c_int(P), ofs.ctypes, Ab.ctypes, C.c_double(dt), sig.ctypes,
+                          C.byref(cost), co.ctypes, C.byref(nodes))
+    return rc, cost.value, co.reshape(N, 12), sig, nodes.value
+
+
+def dt_initial(x0, xf, lim, N):
+    return lib().fqo_dt_initial(_a(x0, 9), _a(xf, 9), _a(lim, 3), N)
+
+
+def gen_new_traj(N, x0, xf, lim, polys, DC, f_init, f_final, f_inc, sigma_list=None, force_final=True):
+    """-> dict(solved, dt, factor, trials, sigma, cost, coeffs)."""
+    L = lib()
+    P, ofs, Ab = pack_polys(polys)
+    if sigma_list is not None:
+        sl = np.ascontiguousarray(np.asarray(sigma_list, np.uint8).reshape(-1, N))
+        ns, slp = sl.shape[0], sl.ctypes
+    else:
+        ns, slp = 0, None
+    dt = C.c_double(0)
+    fac = C.c_double(0)
+    tr = C.c_int(0)
+    cost = C.c_double(np.inf)
+    sig = np.zeros(N, np.uint8)
+    co = np.zeros(12 * N)
+    rc = L.fqo_gen_new_traj(C.c_int(N), C.c_int(int(force_final)), _a(x0, 9).ctypes, _a(xf, 9).ctypes,
+                            _a(lim, 3).ctypes, C.c_int(P), ofs.ctypes, Ab.ctypes, C.c_double(DC),
+                            C.c_double(f_init), C.c_double(f_final), C.c_double(f_inc), C.c_int(ns), slp,
+                            C.byref(dt), C.byref(fac), C.byref(tr), sig.ctypes, C.byref(cost), co.ctypes)
+    return dict(solved=bool(rc), dt=dt.value, factor=fac.value, trials=tr.value, sigma=sig, cost=cost.value,
+                coeffs=co.reshape(N, 12))
+
+
+def fill_x(N, coeffs, dt, DC):
+    L = lib()
+    n = L.fqo_num_samples(N, dt, DC)
+    out = np.zeros((n, 12))
+    L.fqo_fill_x(N, np.ascontiguousarray(coeffs, np.float64).reshape(-1), dt, DC, n, out.reshape(-1))
+    return out
