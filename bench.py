@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- candidate (whole+safe pair) trajectory solves per second.
+
+Workload ("cfg2-pairs"): C corridor problems per GPU; each contributes BASELINE config 2's whole batch
+(N=10, 3 polytopes, 1024 candidates = 16 time allocations x 64 monotone assignments, final position pinned) and a
+safe batch of the same size shaped like config 3 (N=10, 4 polytopes, forceFinalConstraint=false, 16 x 64 of the 286
+monotone assignments).  A "pair" is one whole + one safe candidate solve; a step solves C x 1024 pairs per GPU.
+Multi-GPU: corridors are sharded by rank (weak scaling), one all-gather of the per-candidate costs per step.
+
+value : pairs/s with all inputs resident in HBM (two launches of fq_solve_kernel per step, CUDA-event timed).
+e2e   : pairs/s through the host-pointer C ABI (fq_solve_multi) from pinned host buffers, H2D + D2H inside.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SEG = 10
+N_DT = 16
+N_SIG = 64
+CAND = N_DT * N_SIG
+BYTES_PER_CAND = 8 * (9 + 9 + 3 + 1) + N_SEG + 1 + 8        # x0,xf,lim,dt + sigma + flag + cost = 195 B
+
+
+def make_workload(n_corr, seed0, kind):
+    """kind 'whole' (P=3, force_final) or 'safe' (P=4, free final position).  Returns dict of numpy arrays laid out
+    for fq_solve_multi."""
+    from faster_b200 import capi, corridor as cr
+    P, ff = (3, True) if kind == "whole" else (4, False)
+    sig_all = cr.monotone_sigmas(N_SEG, P)
+    idx = np.linspace(0, len(sig_all) - 1, N_SIG).round().astype(int)
+    sig = sig_all[idx]
+    x0 = np.zeros((n_corr, 9)); xf = np.zeros((n_corr, 9)); lim = np.zeros((n_corr, 3))
+    poly_ofs, face_ofs, rows = [0], [0], []
+    dts = np.zeros((n_corr, CAND)); sigs = np.zeros((n_corr, CAND, N_SEG), np.uint8)
+    probs = []
+    for c in range(n_corr):
+        pb = cr.make_corridor(seed0 + c, P, N_SEG, "uav", ff)
+        probs.append(pb)
+        x0[c], xf[c], lim[c] = pb["x0"], pb["xf"], pb["lim"]
+        for A, b in pb["polys"]:
+            rows.append(np.hstack([A, b[:, None]]))
+            face_ofs.append(face_ofs[-1] + len(b))
+        poly_ofs.append(poly_ofs[-1] + P)
+        dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N_SEG)
+        fac = np.arange(1, N_DT + 1, dtype=np.float64)          # factor sweep 1..16 step 1 (faster.cpp:57, yaml:30)
+        dts[c] = np.repeat(fac * max(dti, 2 * pb["DC"]), N_SIG)
+        sigs[c] = np.tile(sig, (N_DT, 1))
+    w = dict(kind=kind, N=N_SEG, ff=ff, n_prob=n_corr, x0=x0, xf=xf, lim=lim,
+             poly_ofs=np.array(poly_ofs, np.int32), face_ofs=np.array(face_ofs, np.int32),
+             Ab=np.ascontiguousarray(np.vstack(rows)), cand_ofs=(np.arange(n_corr + 1) * CAND).astype(np.int32),
+             dt=dts.reshape(-1), sigma=sigs.reshape(-1, N_SEG), probs=probs,
+             max_faces=int(max(face_ofs[poly_ofs[j + 1]] - face_ofs[poly_ofs[j]] for j in range(n_corr))))
+    return w
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append((float(f[0]), float(f[1]), f[2:]))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i, v in enumerate(s[2]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": self.samples[0][1],
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_rate(n_corr_sample, threads, min_seconds, seed0=900000):
+    """Times the CPU restatement (oracle) on a bounded sample of the same workload.  -> (pairs/s, sample text)."""
+    from oracle import pyoracle as po
+    po.build()
+    ww = make_workload(n_corr_sample, seed0, "whole")
+    ws = make_workload(n_corr_sample, seed0 + 50000, "safe")
+
+    def one_pass():
+        for w in (ww, ws):
+            for c, pb in enumerate(w["probs"]):
+                a, b = c * CAND, (c + 1) * CAND
+                po.solve_batch(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], w["dt"][a:b], w["sigma"][a:b],
+                               w["ff"], False, threads)
+    one_pass()                                                      # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        one_pass()
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= min_seconds and reps >= 2:
+            break
+    rate = reps * n_corr_sample * CAND / el
+    return rate, "%d corridors x %d pairs, %d passes, %.1f s" % (n_corr_sample, CAND, reps, el)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path cannot run (Gurobi is closed source and
+    absent); this times the CPU restatement of it (oracle/fq_oracle.c) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_s = max(1, args.ref_corridors)
+    from oracle import pyoracle as po
+    po.build()
+    ww = make_workload(n_s, 900000, "whole")
+    ws = make_workload(n_s, 950000, "safe")
+
+    def step():
+        for w in (ww, ws):
+            for c, pb in enumerate(w["probs"]):
+                a, b = c * CAND, (c + 1) * CAND
+                po.solve_batch(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], w["dt"][a:b], w["sigma"][a:b],
+                               w["ff"], False, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = args.steps * n_s * CAND / el
+    line = {"impl": "reference", "metric": "candidate (whole+safe pair) trajectory solves/sec", "value": value,
+            "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2-pairs: N=10, whole P=3 + safe P=4, 1024 pairs/corridor (16 dt x 64 sigma)",
+                       "corridors_per_step": n_s, "note": "CPU restatement of SolverGurobi (Gurobi itself unavailable)"},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": "%d corridors x %d pairs per step" % (n_s, CAND)},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--corridors", type=int, default=64, help="corridor problems per GPU per step")
+    ap.add_argument("--ref-corridors", type=int, default=16, help="corridors per step of the CPU arm (bounded sample)")
+    ap.add_argument("--cpu-seconds", type=float, default=6.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from faster_b200 import capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    solver = capi.Solver(local)
+    C = args.corridors
+    works = [make_workload(C, 10000 * (rank + 1), "whole"), make_workload(C, 10000 * (rank + 1) + 5000, "safe")]
+    n_cand = C * CAND
+
+    # ---- pinned host copies (e2e path) and device-resident copies (value path)
+    keys = ["x0", "xf", "lim", "poly_ofs", "face_ofs", "Ab", "cand_ofs", "dt", "sigma"]
+    host, devt, outs_h, outs_d = [], [], [], []
+    for w in works:
+        h = {k: torch.from_numpy(np.ascontiguousarray(w[k])).pin_memory() for k in keys}
+        host.append(h)
+        devt.append({k: v.to(dev) for k, v in h.items()})
+        outs_h.append((torch.zeros(n_cand, dtype=torch.uint8).pin_memory(), torch.zeros(n_cand, dtype=torch.float64).pin_memory()))
+        outs_d.append((torch.zeros(n_cand, dtype=torch.uint8, device=dev), torch.zeros(n_cand, dtype=torch.float64, device=dev),
+                       torch.zeros(n_cand, dtype=torch.int32, device=dev)))
+    gathered = torch.zeros(world * 2 * n_cand, dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_resident(with_iters=False):
+        for w, d, o in zip(works, devt, outs_d):
+            solver.solve_multi_dev(w["N"], w["ff"], w["n_prob"], d["x0"].data_ptr(), d["xf"].data_ptr(),
+                                   d["lim"].data_ptr(), d["poly_ofs"].data_ptr(), d["face_ofs"].data_ptr(),
+                                   d["Ab"].data_ptr(), d["cand_ofs"].data_ptr(), CAND, w["max_faces"],
+                                   d["dt"].data_ptr(), d["sigma"].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), 0,
+                                   o[2].data_ptr() if with_iters else 0, stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, torch.cat([outs_d[0][1], outs_d[1][1]]))
+
+    def step_e2e():
+        for w, h, o in zip(works, host, outs_h):
+            solver.solve_multi(w["N"], w["ff"], h["x0"].numpy(), h["xf"].numpy(), h["lim"].numpy(),
+                               h["poly_ofs"].numpy(), h["face_ofs"].numpy(), h["Ab"].numpy(), h["cand_ofs"].numpy(),
+                               h["dt"].numpy(), h["sigma"].numpy(), out=(o[0].numpy(), o[1].numpy(), None, None))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()                                              # L2 flush between timed steps (outside the events)
+        ev[i][0].record()
+        kev[i][0].record()
+        step_resident()
+        ev[i][1].record()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    # per-launch kernel time: time the two solve launches alone (no collective)
+    barrier()
+    kms = []
+    for i in range(min(args.steps, 10)):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for w, d, o in zip(works, devt, outs_d):
+            solver.solve_multi_dev(w["N"], w["ff"], w["n_prob"], d["x0"].data_ptr(), d["xf"].data_ptr(),
+                                   d["lim"].data_ptr(), d["poly_ofs"].data_ptr(), d["face_ofs"].data_ptr(),
+                                   d["Ab"].data_ptr(), d["cand_ofs"].data_ptr(), CAND, w["max_faces"],
+                                   d["dt"].data_ptr(), d["sigma"].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), 0, 0, stream)
+        b.record()
+        torch.cuda.synchronize()
+        kms.append(a.elapsed_time(b) / 2.0)
+    kernel_ms = float(np.mean(kms))
+    # ---- e2e timing (host buffers, copies inside)
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    # iteration statistics (one extra, untimed launch) and a sanity check that e2e and resident paths agree
+    step_resident(with_iters=True)
+    torch.cuda.synchronize()
+    iters = torch.cat([outs_d[0][2], outs_d[1][2]]).abs().double()
+    feas_frac = float(torch.cat([outs_d[0][0], outs_d[1][0]]).double().mean())
+    same = all(bool(torch.equal(outs_d[k][0].cpu(), outs_h[k][0])) for k in range(2))
+
+    t = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s, kernel_ms = [float(x) for x in t.cpu()]
+    pairs_per_step = world * C * CAND
+    value = pairs_per_step * args.steps / (total_ms * 1e-3)
+    e2e = pairs_per_step * args.steps / e2e_s
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = n_cand * BYTES_PER_CAND / (kernel_ms * 1e-3) / 1e9
+        h2d = sum(int(h[k].numel() * h[k].element_size()) for h in host for k in keys)
+        d2h = sum(int(o[0].numel() + 8 * o[1].numel()) for o in outs_h)
+        line = {"metric": "candidate (whole+safe pair) trajectory solves/sec", "value": value, "unit": "pairs/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "cfg2-pairs: N=10, whole P=3 + safe P=4, 1024 pairs/corridor (16 dt x 64 sigma)",
+                           "corridors_per_gpu": C, "pairs_per_step": pairs_per_step,
+                           "l2": "flushed between timed steps (256 MiB memset outside the per-step events)",
+                           "parallelism": "corridor shards per rank, all-gather of costs" if world > 1 else "single GPU",
+                           "feasible_fraction": feas_frac, "mean_active_set_iters": float(iters.mean()),
+                           "e2e_matches_resident": same},
+                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": 2 * args.steps,
+                "clocks": sampler.summary(),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "fq_solve_kernel", "kernel_ms": kernel_ms,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                             "algorithmic_bytes_per_candidate": BYTES_PER_CAND,
+                             "note": "compute/latency-bound FP64 kernel; HBM fraction is tiny by construction (SURVEY 8d)"}}
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, sample = cpu_reference_rate(4, threads, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

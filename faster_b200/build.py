@@ -1,0 +1,41 @@
+"""Builds faster_b200/lib/libfaster_b200.so (CUDA kernels + C ABI + host helpers) for sm_100a with nvcc.
+
+In-tree build: the .so is git-ignored but travels to the GPU box with the snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libfaster_b200.so")
+SOURCES = ["fq_kernels.cu", "fq_capi.cu", "fq_host.cpp"]
+HEADERS = ["fq_kernels.cuh", "fq_plan.h", os.path.join("..", "..", "include", "faster_b200.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-cudart", "static"]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS) or \
+        os.path.getmtime(os.path.abspath(__file__)) > t
+
+
+def build(force=False, verbose=False):
+    if not (force or _stale()):
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

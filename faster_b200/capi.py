@@ -1,0 +1,189 @@
+"""ctypes binding of the C ABI in include/faster_b200.h (what a cgo/JNI-style binding of the reference side would
+bind).  Used by tests and bench.py.  There is no CPU fallback: if the shared library is missing
+or no GPU is present, calls raise.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfaster_b200.so")
+_lib = None
+
+EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_solve_batch", "fq_solve_multi",
+           "fq_solve_multi_dev", "fq_gen_new_traj", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
+           "fq_monotone_sigmas", "fq_plan_tables"]
+
+
+class FqError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FqError("%s is missing: run `python -m faster_b200.build` (no CPU fallback exists)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.fq_last_error.restype = C.c_char_p
+        L.fq_last_error.argtypes = [C.c_void_p]
+        L.fq_dt_initial.restype = C.c_double
+        L.fq_dt_initial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.fq_num_samples.restype = C.c_int
+        L.fq_num_samples.argtypes = [C.c_int, C.c_double, C.c_double]
+        L.fq_fill_x.restype = None
+        L.fq_fill_x.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
+        L.fq_monotone_sigmas.restype = C.c_long
+        L.fq_monotone_sigmas.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_long]
+        L.fq_plan_tables.restype = C.c_int
+        L.fq_plan_tables.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fq_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.fq_destroy.argtypes = [C.c_void_p]
+        L.fq_destroy.restype = None
+        L.fq_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        L.fq_solve_multi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 13
+        L.fq_solve_multi_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7 + \
+                                        [C.c_int, C.c_int] + [C.c_void_p] * 7
+        L.fq_gen_new_traj.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + \
+                                     [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        _lib = L
+    return _lib
+
+
+def _f64(x, n=None):
+    x = np.ascontiguousarray(np.asarray(x, np.float64).reshape(-1))
+    if n is not None and x.size != n:
+        raise ValueError("expected %d doubles, got %d" % (n, x.size))
+    return x
+
+
+def pack_polys(polys):
+    """list of (A[F,3], b[F]) -> (P, face_ofs int32[P+1], Ab float64[SF,4])."""
+    ofs, rows = [0], []
+    for A, b in polys:
+        A = np.asarray(A, np.float64).reshape(-1, 3)
+        b = np.asarray(b, np.float64).reshape(-1)
+        rows.append(np.hstack([A, b[:, None]]))
+        ofs.append(ofs[-1] + A.shape[0])
+    Ab = np.ascontiguousarray(np.vstack(rows), np.float64) if rows else np.zeros((1, 4))
+    return len(polys), np.asarray(ofs, np.int32), Ab
+
+
+def dt_initial(x0, xf, lim, N):
+    a, b, c = _f64(x0, 9), _f64(xf, 9), _f64(lim, 3)
+    return lib().fq_dt_initial(a.ctypes.data, b.ctypes.data, c.ctypes.data, int(N))
+
+
+def num_samples(N, dt, DC):
+    return lib().fq_num_samples(int(N), float(dt), float(DC))
+
+
+def fill_x(N, coeffs, dt, DC):
+    n = num_samples(N, dt, DC)
+    co = _f64(coeffs, 12 * N)
+    out = np.zeros((n, 12))
+    lib().fq_fill_x(int(N), co.ctypes.data, float(dt), float(DC), n, out.ctypes.data)
+    return out
+
+
+def monotone_sigmas(N, P):
+    n = lib().fq_monotone_sigmas(int(N), int(P), None, 0)
+    out = np.zeros((n, N), np.uint8)
+    lib().fq_monotone_sigmas(int(N), int(P), out.ctypes.data, n)
+    return out
+
+
+def plan_tables(N, force_final):
+    ne = 3 if force_final else 2
+    nz, NY = N - ne, 6 * N + 1
+    TZ = np.zeros((NY, max(nz, 0)))
+    T0 = np.zeros((NY, 3 + ne))
+    FT = np.zeros((ne, 3))
+    r = lib().fq_plan_tables(int(N), int(bool(force_final)), TZ.ctypes.data, T0.ctypes.data, FT.ctypes.data)
+    if r == 0:
+        raise FqError("unsupported (N, force_final)")
+    return TZ, T0, FT
+
+
+class Solver:
+    """Owns an fq_ctx on one GPU."""
+
+    def __init__(self, device=0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.fq_create(C.byref(h), int(device))
+        if rc != 0:
+            raise FqError("fq_create failed (%d): %s" % (rc, self._L.fq_last_error(None).decode()))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.fq_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise FqError("faster_b200 error %d: %s" % (rc, self._L.fq_last_error(self._h).decode()))
+        return rc
+
+    def solve_batch(self, N, x0, xf, lim, polys, dts, sigmas, force_final=True, want_coeffs=False, want_iters=False):
+        P, ofs, Ab = pack_polys(polys)
+        dts = _f64(dts)
+        n = dts.size
+        sig = np.ascontiguousarray(np.asarray(sigmas, np.uint8).reshape(n, N)) if P > 0 else np.zeros((n, N), np.uint8)
+        x0, xf, lim = _f64(x0, 9), _f64(xf, 9), _f64(lim, 3)
+        feas = np.zeros(n, np.uint8)
+        cost = np.zeros(n)
+        co = np.zeros((n, N, 12)) if want_coeffs else None
+        it = np.zeros(n, np.int32) if want_iters else None
+        self._check(self._L.fq_solve_batch(self._h, int(N), int(bool(force_final)), x0.ctypes.data, xf.ctypes.data,
+                                           lim.ctypes.data, P, ofs.ctypes.data, Ab.ctypes.data, n, dts.ctypes.data,
+                                           sig.ctypes.data, feas.ctypes.data, cost.ctypes.data,
+                                           co.ctypes.data if want_coeffs else None,
+                                           it.ctypes.data if want_iters else None))
+        return feas, cost, co, it
+
+    def solve_multi(self, N, force_final, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dts, sigmas,
+                    want_coeffs=False, want_iters=False, out=None):
+        """Arrays as in fq_solve_multi; numpy (possibly pinned torch-backed) host arrays."""
+        n_prob = len(cand_ofs) - 1
+        n = int(cand_ofs[-1])
+        if out is None:
+            feas = np.zeros(n, np.uint8)
+            cost = np.zeros(n)
+            co = np.zeros((n, N, 12)) if want_coeffs else None
+            it = np.zeros(n, np.int32) if want_iters else None
+        else:
+            feas, cost, co, it = out
+        self._check(self._L.fq_solve_multi(self._h, int(N), int(bool(force_final)), n_prob, x0.ctypes.data,
+                                           xf.ctypes.data, lim.ctypes.data, poly_ofs.ctypes.data, face_ofs.ctypes.data,
+                                           Ab.ctypes.data, cand_ofs.ctypes.data, dts.ctypes.data, sigmas.ctypes.data,
+                                           feas.ctypes.data, cost.ctypes.data,
+                                           co.ctypes.data if co is not None else None,
+                                           it.ctypes.data if it is not None else None))
+        return feas, cost, co, it
+
+    def solve_multi_dev(self, N, force_final, n_prob, d_x0, d_xf, d_lim, d_poly_ofs, d_face_ofs, d_Ab, d_cand_ofs,
+                        max_cand, max_faces, d_dt, d_sigma, d_feas, d_cost, d_coeffs=0, d_iters=0, stream=0):
+        """All d_* are integer device addresses (e.g. torch tensor .data_ptr())."""
+        self._check(self._L.fq_solve_multi_dev(self._h, int(N), int(bool(force_final)), int(n_prob), d_x0, d_xf,
+                                               d_lim, d_poly_ofs, d_face_ofs, d_Ab, d_cand_ofs, int(max_cand),
+                                               int(max_faces), d_dt, d_sigma, d_feas, d_cost, d_coeffs or None,
+                                               d_iters or None, stream or None))
+
+    def gen_new_traj(self, N, x0, xf, lim, polys, dts, sigmas, force_final=True):
+        """-> dict(solved, dt_index, sigma_index, cost, coeffs[N,12])."""
+        P, ofs, Ab = pack_polys(polys)
+        dts = _f64(dts)
+        sig = np.ascontiguousarray(np.asarray(sigmas, np.uint8).reshape(-1, N)) if P > 0 else np.zeros((1, N), np.uint8)
+        x0, xf, lim = _f64(x0, 9), _f64(xf, 9), _f64(lim, 3)
+        di, si, cost = C.c_int(-1), C.c_int(-1), C.c_double(np.inf)
+        co = np.zeros((N, 12))
+        rc = self._check(self._L.fq_gen_new_traj(self._h, int(N), int(bool(force_final)), x0.ctypes.data,
+                                                 xf.ctypes.data, lim.ctypes.data, P, ofs.ctypes.data, Ab.ctypes.data,
+                                                 dts.size, dts.ctypes.data, sig.shape[0], sig.ctypes.data,
+                                                 C.addressof(di), C.addressof(si), C.addressof(cost), co.ctypes.data))
+        return dict(solved=bool(rc), dt_index=di.value, sigma_index=si.value, cost=cost.value, coeffs=co)

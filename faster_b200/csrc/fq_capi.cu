@@ -1,0 +1,427 @@
+// C ABI of faster_b200 (see include/faster_b200.h): context, plan cache, host<->device staging, launches.
+#include "../../include/faster_b200.h"
+#include "fq_kernels.cuh"
+#include "fq_plan.h"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace
+{
+struct PlanDev
+{
+  FqPlanHost h;
+  double *TZ = nullptr, *T0 = nullptr, *FT = nullptr;
+};
+
+struct Arena
+{ // grow-only device buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 4 + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinnedArena
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+std::string g_create_error;
+}  // namespace
+
+struct fq_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::map<int, PlanDev> plans;   // key N*2+force_final
+  Arena d_in, d_out;
+  PinnedArena h_in, h_out;
+  std::string err;
+};
+
+namespace
+{
+int fail(fq_ctx* c, int code, const std::string& msg)
+{
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+int cuda_fail(fq_ctx* c, cudaError_t e, const char* what)
+{
+  return fail(c, FQ_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define FQ_CUDA(call)                                          \
+  do {                                                         \
+    cudaError_t e__ = (call);                                  \
+    if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+  } while (0)
+
+int get_plan(fq_ctx* ctx, int N, int force_final, PlanDev** out)
+{
+  const int key = N * 2 + (force_final ? 1 : 0);
+  auto it = ctx->plans.find(key);
+  if (it == ctx->plans.end())
+  {
+    PlanDev pd;
+    if (!fq_build_plan(N, force_final ? 1 : 0, &pd.h))
+      return fail(ctx, FQ_E_ARG, "unsupported N (need ne <= N <= FQ_MAX_N)");
+    FQ_CUDA(cudaMalloc(&pd.TZ, sizeof(double) * (pd.h.TZ.size() + 1)));
+    FQ_CUDA(cudaMalloc(&pd.T0, sizeof(double) * pd.h.T0.size()));
+    FQ_CUDA(cudaMalloc(&pd.FT, sizeof(double) * pd.h.FT.size()));
+    FQ_CUDA(cudaMemcpy(pd.TZ, pd.h.TZ.data(), sizeof(double) * pd.h.TZ.size(), cudaMemcpyHostToDevice));
+    FQ_CUDA(cudaMemcpy(pd.T0, pd.h.T0.data(), sizeof(double) * pd.h.T0.size(), cudaMemcpyHostToDevice));
+    FQ_CUDA(cudaMemcpy(pd.FT, pd.h.FT.data(), sizeof(double) * pd.h.FT.size(), cudaMemcpyHostToDevice));
+    it = ctx->plans.emplace(key, pd).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+void fill_plan_args(const PlanDev& pd, FqKernelArgs* a)
+{
+  a->N = pd.h.N; a->force_final = pd.h.force_final; a->ne = pd.h.ne; a->nz = pd.h.nz;
+  a->nw = 3 * pd.h.nz; a->NY = pd.h.NY; a->ld = (3 * pd.h.nz) | 1;
+  a->TZ = pd.TZ; a->T0 = pd.T0; a->FT = pd.FT;
+}
+
+inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+}  // namespace
+
+extern "C" int fq_create(fq_ctx** out, int device)
+{
+  if (!out) return fail(nullptr, FQ_E_ARG, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(nullptr, FQ_E_NOGPU, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
+                                         " (faster_b200 has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(nullptr, FQ_E_ARG, "device index out of range");
+  fq_ctx* ctx = new (std::nothrow) fq_ctx();
+  if (!ctx) return fail(nullptr, FQ_E_NOMEM, "out of host memory");
+  ctx->device = device;
+  e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess)
+  {
+    std::string msg = std::string("cuda init: ") + cudaGetErrorString(e);
+    delete ctx;
+    return fail(nullptr, FQ_E_CUDA, msg);
+  }
+  *out = ctx;
+  return 0;
+}
+
+extern "C" void fq_destroy(fq_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& kv : ctx->plans) { cudaFree(kv.second.TZ); cudaFree(kv.second.T0); cudaFree(kv.second.FT); }
+  ctx->d_in.release(); ctx->d_out.release(); ctx->h_in.release(); ctx->h_out.release();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* fq_last_error(const fq_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+namespace
+{
+// common launch: every pointer is a device pointer
+int launch_solve(fq_ctx* ctx, int N, int force_final, int n_prob, const double* d_x0, const double* d_xf,
+                 const double* d_lim, const int* d_poly_ofs, const int* d_face_ofs, const double* d_Ab,
+                 const int* d_cand_ofs, int max_cand, int max_faces, const double* d_dt, const uint8_t* d_sigma,
+                 uint8_t* d_feasible, double* d_cost, double* d_coeffs, int32_t* d_iters, cudaStream_t stream)
+{
+  PlanDev* pd = nullptr;
+  int rc = get_plan(ctx, N, force_final, &pd);
+  if (rc) return rc;
+  FqKernelArgs a;
+  fill_plan_args(*pd, &a);
+  a.n_prob = n_prob; a.x0 = d_x0; a.xf = d_xf; a.lim = d_lim; a.poly_ofs = d_poly_ofs; a.face_ofs = d_face_ofs;
+  a.Ab = d_Ab; a.max_faces = max_faces > 0 ? max_faces : 1; a.cand_ofs = d_cand_ofs; a.dt = d_dt; a.sigma = d_sigma;
+  a.feasible = d_feasible; a.cost = d_cost; a.coeffs = d_coeffs; a.iters = d_iters;
+  if (fq_solve_smem_bytes(a) > 227 * 1024)
+    return fail(ctx, FQ_E_ARG, "problem too large for shared memory (N / faces per problem)");
+  FQ_CUDA(fq_launch_solve(a, max_cand, stream));
+  return 0;
+}
+}  // namespace
+
+extern "C" int fq_solve_multi_dev(fq_ctx* ctx, int N, int force_final, int n_prob, const double* d_x0,
+                                  const double* d_xf, const double* d_lim, const int* d_poly_ofs,
+                                  const int* d_face_ofs, const double* d_Ab, const int* d_cand_ofs,
+                                  int max_cand_per_prob, int max_faces_per_prob, const double* d_dt,
+                                  const uint8_t* d_sigma, uint8_t* d_feasible, double* d_cost, double* d_coeffs,
+                                  int32_t* d_iters, void* stream)
+{
+  if (!ctx) return FQ_E_ARG;
+  if (n_prob < 0 || max_cand_per_prob < 0) return fail(ctx, FQ_E_ARG, "negative count");
+  if (n_prob == 0 || max_cand_per_prob == 0) return 0;
+  if (((uintptr_t)d_Ab & 15) != 0) return fail(ctx, FQ_E_ARG, "Ab must be 16-byte aligned");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  return launch_solve(ctx, N, force_final, n_prob, d_x0, d_xf, d_lim, d_poly_ofs, d_face_ofs, d_Ab, d_cand_ofs,
+                      max_cand_per_prob, max_faces_per_prob, d_dt, d_sigma, d_feasible, d_cost, d_coeffs, d_iters,
+                      stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+namespace
+{
+struct HostLayout
+{ // byte offsets of each array inside the input / output arenas
+  size_t x0, xf, lim, dt, Ab, poly_ofs, face_ofs, cand_ofs, sigma, in_bytes;
+  size_t cost, coeffs, iters, feasible, out_bytes;
+};
+
+// validates the host description and computes sizes
+int describe(fq_ctx* ctx, int N, int force_final, int n_prob, const int* poly_ofs, const int* face_ofs,
+             const int* cand_ofs, const uint8_t* sigma, bool want_coeffs, bool want_iters, HostLayout* L,
+             int* n_cand, int* n_poly, int* n_face, int* max_cand, int* max_faces)
+{
+  const int ne = force_final ? 3 : 2;
+  if (N < ne || N > FQ_MAX_N) return fail(ctx, FQ_E_ARG, "N out of range");
+  if (n_prob <= 0) return fail(ctx, FQ_E_ARG, "n_prob <= 0");
+  if (poly_ofs[0] != 0 || cand_ofs[0] != 0 || face_ofs[0] != 0) return fail(ctx, FQ_E_ARG, "offset arrays must start at 0");
+  *max_cand = 0; *max_faces = 0;
+  for (int j = 0; j < n_prob; j++)
+  {
+    const int P = poly_ofs[j + 1] - poly_ofs[j], nc = cand_ofs[j + 1] - cand_ofs[j];
+    if (P < 0 || P > FQ_MAX_POLY) return fail(ctx, FQ_E_ARG, "polytope count out of range (0..FQ_MAX_POLY)");
+    if (nc < 0) return fail(ctx, FQ_E_ARG, "cand_ofs not monotone");
+    const int nf = face_ofs[poly_ofs[j + 1]] - face_ofs[poly_ofs[j]];
+    if (nf < 0) return fail(ctx, FQ_E_ARG, "face_ofs not monotone");
+    for (int p = poly_ofs[j]; p < poly_ofs[j + 1]; p++)
+      if (face_ofs[p + 1] < face_ofs[p]) return fail(ctx, FQ_E_ARG, "face_ofs not monotone");
+    if (P > 0 && sigma)
+      for (size_t i = (size_t)cand_ofs[j] * N; i < (size_t)cand_ofs[j + 1] * N; i++)
+        if (sigma[i] >= P) return fail(ctx, FQ_E_ARG, "sigma entry >= number of polytopes");
+    if (nc > *max_cand) *max_cand = nc;
+    if (nf > *max_faces) *max_faces = nf;
+  }
+  *n_cand = cand_ofs[n_prob]; *n_poly = poly_ofs[n_prob]; *n_face = face_ofs[*n_poly];
+  size_t o = 0;
+  L->Ab = o;        o = align16(o + sizeof(double) * 4 * (size_t)(*n_face > 0 ? *n_face : 1));
+  L->x0 = o;        o += sizeof(double) * 9 * (size_t)n_prob;
+  L->xf = o;        o += sizeof(double) * 9 * (size_t)n_prob;
+  L->lim = o;       o += sizeof(double) * 3 * (size_t)n_prob;
+  L->dt = o;        o += sizeof(double) * (size_t)*n_cand;
+  L->poly_ofs = o;  o += sizeof(int) * (size_t)(n_prob + 1);
+  L->face_ofs = o;  o += sizeof(int) * (size_t)(*n_poly + 1);
+  L->cand_ofs = o;  o += sizeof(int) * (size_t)(n_prob + 1);
+  L->sigma = o;     o += (size_t)*n_cand * N;
+  L->in_bytes = align16(o);
+  o = 0;
+  L->cost = o;      o += sizeof(double) * (size_t)*n_cand;
+  L->coeffs = o;    o += want_coeffs ? sizeof(double) * 12 * (size_t)N * (size_t)*n_cand : 0;
+  L->iters = o;     o += want_iters ? sizeof(int32_t) * (size_t)*n_cand : 0;
+  L->feasible = o;  o += (size_t)*n_cand;
+  L->out_bytes = align16(o);
+  return 0;
+}
+
+constexpr size_t kPackThreshold = 512 * 1024;   // below this, inputs are packed into one pinned staging copy
+}  // namespace
+
+extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf,
+                              const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
+                              const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible,
+                              double* cost, double* coeffs, int32_t* iters)
+{
+  if (!ctx) return FQ_E_ARG;
+  if (!x0 || !xf || !lim || !poly_ofs || !face_ofs || !cand_ofs || !dt || !feasible || !cost)
+    return fail(ctx, FQ_E_ARG, "NULL argument");
+  HostLayout L;
+  int n_cand, n_poly, n_face, max_cand, max_faces;
+  int rc = describe(ctx, N, force_final, n_prob, poly_ofs, face_ofs, cand_ofs, sigma, coeffs != nullptr,
+                    iters != nullptr, &L, &n_cand, &n_poly, &n_face, &max_cand, &max_faces);
+  if (rc) return rc;
+  if (n_cand == 0) return 0;
+  if (n_poly > 0 && (!Ab || !sigma)) return fail(ctx, FQ_E_ARG, "polytopes given but Ab or sigma is NULL");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  FQ_CUDA(ctx->d_in.reserve(L.in_bytes));
+  FQ_CUDA(ctx->d_out.reserve(L.out_bytes));
+  char* din = (char*)ctx->d_in.p;
+  char* dout = (char*)ctx->d_out.p;
+  cudaStream_t st = ctx->stream;
+  const size_t sig_bytes = (size_t)n_cand * N;
+  struct Piece { size_t off; const void* src; size_t bytes; };
+  const Piece pieces[] = {
+    { L.Ab, Ab, sizeof(double) * 4 * (size_t)n_face }, { L.x0, x0, sizeof(double) * 9 * (size_t)n_prob },
+    { L.xf, xf, sizeof(double) * 9 * (size_t)n_prob }, { L.lim, lim, sizeof(double) * 3 * (size_t)n_prob },
+    { L.dt, dt, sizeof(double) * (size_t)n_cand },     { L.poly_ofs, poly_ofs, sizeof(int) * (size_t)(n_prob + 1) },
+    { L.face_ofs, face_ofs, sizeof(int) * (size_t)(n_poly + 1) },
+    { L.cand_ofs, cand_ofs, sizeof(int) * (size_t)(n_prob + 1) }, { L.sigma, sigma, n_poly > 0 ? sig_bytes : 0 },
+  };
+  if (L.in_bytes <= kPackThreshold)
+  { // latency path: one pinned staging buffer, one H2D copy
+    FQ_CUDA(ctx->h_in.reserve(L.in_bytes));
+    for (const Piece& p : pieces)
+      if (p.bytes) std::memcpy((char*)ctx->h_in.p + p.off, p.src, p.bytes);
+    FQ_CUDA(cudaMemcpyAsync(din, ctx->h_in.p, L.in_bytes, cudaMemcpyHostToDevice, st));
+  }
+  else
+  { // throughput path: DMA straight from the caller's buffers (true async when they are pinned)
+    for (const Piece& p : pieces)
+      if (p.bytes) FQ_CUDA(cudaMemcpyAsync(din + p.off, p.src, p.bytes, cudaMemcpyHostToDevice, st));
+  }
+  if (n_poly == 0) FQ_CUDA(cudaMemsetAsync(din + L.sigma, 0, sig_bytes, st));
+  rc = launch_solve(ctx, N, force_final, n_prob, (const double*)(din + L.x0), (const double*)(din + L.xf),
+                    (const double*)(din + L.lim), (const int*)(din + L.poly_ofs), (const int*)(din + L.face_ofs),
+                    (const double*)(din + L.Ab), (const int*)(din + L.cand_ofs), max_cand, max_faces,
+                    (const double*)(din + L.dt), (const uint8_t*)(din + L.sigma), (uint8_t*)(dout + L.feasible),
+                    (double*)(dout + L.cost), coeffs ? (double*)(dout + L.coeffs) : nullptr,
+                    iters ? (int32_t*)(dout + L.iters) : nullptr, st);
+  if (rc) return rc;
+  if (L.out_bytes <= kPackThreshold)
+  {
+    FQ_CUDA(ctx->h_out.reserve(L.out_bytes));
+    FQ_CUDA(cudaMemcpyAsync(ctx->h_out.p, dout, L.out_bytes, cudaMemcpyDeviceToHost, st));
+    FQ_CUDA(cudaStreamSynchronize(st));
+    const char* ho = (const char*)ctx->h_out.p;
+    std::memcpy(cost, ho + L.cost, sizeof(double) * (size_t)n_cand);
+    std::memcpy(feasible, ho + L.feasible, (size_t)n_cand);
+    if (coeffs) std::memcpy(coeffs, ho + L.coeffs, sizeof(double) * 12 * (size_t)N * n_cand);
+    if (iters) std::memcpy(iters, ho + L.iters, sizeof(int32_t) * (size_t)n_cand);
+  }
+  else
+  {
+    FQ_CUDA(cudaMemcpyAsync(cost, dout + L.cost, sizeof(double) * (size_t)n_cand, cudaMemcpyDeviceToHost, st));
+    FQ_CUDA(cudaMemcpyAsync(feasible, dout + L.feasible, (size_t)n_cand, cudaMemcpyDeviceToHost, st));
+    if (coeffs)
+      FQ_CUDA(cudaMemcpyAsync(coeffs, dout + L.coeffs, sizeof(double) * 12 * (size_t)N * n_cand, cudaMemcpyDeviceToHost, st));
+    if (iters)
+      FQ_CUDA(cudaMemcpyAsync(iters, dout + L.iters, sizeof(int32_t) * (size_t)n_cand, cudaMemcpyDeviceToHost, st));
+    FQ_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" int fq_solve_batch(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf,
+                              const double* lim, int P, const int* face_ofs, const double* Ab, int n_cand,
+                              const double* dt, const uint8_t* sigma, uint8_t* feasible, double* cost,
+                              double* coeffs, int32_t* iters)
+{
+  if (!ctx) return FQ_E_ARG;
+  if (P < 0 || n_cand < 0) return fail(ctx, FQ_E_ARG, "negative count");
+  const int poly_ofs[2] = { 0, P }, cand_ofs[2] = { 0, n_cand }, zero_face[1] = { 0 };
+  return fq_solve_multi(ctx, N, force_final, 1, x0, xf, lim, poly_ofs, P > 0 ? face_ofs : zero_face, Ab, cand_ofs, dt,
+                        sigma, feasible, cost, coeffs, iters);
+}
+
+extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf,
+                               const double* lim, int P, const int* face_ofs, const double* Ab, int n_dt,
+                               const double* dts, int n_sigma, const uint8_t* sigmas, int* dt_index,
+                               int* sigma_index, double* cost, double* coeffs)
+{
+  if (!ctx) return FQ_E_ARG;
+  if (!x0 || !xf || !lim || !dts) return fail(ctx, FQ_E_ARG, "NULL argument");
+  if (P < 0 || P > FQ_MAX_POLY || n_dt <= 0) return fail(ctx, FQ_E_ARG, "bad P or n_dt");
+  if (P == 0) n_sigma = 1;
+  if (n_sigma <= 0 || (P > 0 && (!sigmas || !face_ofs || !Ab))) return fail(ctx, FQ_E_ARG, "bad sigma list / polytopes");
+  if (n_sigma > (1 << 20)) return fail(ctx, FQ_E_ARG, "n_sigma > 2^20");
+  const int ne = force_final ? 3 : 2;
+  if (N < ne || N > FQ_MAX_N) return fail(ctx, FQ_E_ARG, "N out of range");
+  const long long n_cand_ll = (long long)n_dt * n_sigma;
+  if (n_cand_ll > (1LL << 30)) return fail(ctx, FQ_E_ARG, "too many candidates");
+  const int n_cand = (int)n_cand_ll;
+  const int n_face = P > 0 ? face_ofs[P] : 0;
+  if (P > 0)
+    for (size_t i = 0; i < (size_t)n_sigma * N; i++)
+      if (sigmas[i] >= P) return fail(ctx, FQ_E_ARG, "sigma entry >= number of polytopes");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  // ---- pack the (small) problem description; the dt x sigma grid is expanded on the host side of the copy
+  size_t o = 0;
+  const size_t oAb = o;   o = align16(o + sizeof(double) * 4 * (size_t)(n_face > 0 ? n_face : 1));
+  const size_t ox0 = o;   o += sizeof(double) * 9;
+  const size_t oxf = o;   o += sizeof(double) * 9;
+  const size_t olim = o;  o += sizeof(double) * 3;
+  const size_t odt = o;   o += sizeof(double) * (size_t)n_cand;
+  const size_t opo = o;   o += sizeof(int) * 2;
+  const size_t ofo = o;   o += sizeof(int) * (size_t)(P + 1);
+  const size_t oco = o;   o += sizeof(int) * 2;
+  const size_t osig = o;  o += (size_t)n_cand * N;
+  const size_t in_bytes = align16(o);
+  o = 0;
+  const size_t ocost = o;   o += sizeof(double) * (size_t)n_cand;
+  const size_t ocoef = o;   o += sizeof(double) * 12 * (size_t)N * n_cand;
+  const size_t owin = o;    o += sizeof(double) * (1 + 12 * (size_t)N);     // winner: cost + coeffs
+  const size_t oidx = o;    o += sizeof(int) * 2;
+  const size_t ofeas = o;   o += (size_t)n_cand;
+  const size_t out_bytes = align16(o);
+  FQ_CUDA(ctx->d_in.reserve(in_bytes));
+  FQ_CUDA(ctx->d_out.reserve(out_bytes));
+  FQ_CUDA(ctx->h_in.reserve(in_bytes));
+  FQ_CUDA(ctx->h_out.reserve(sizeof(double) * (1 + 12 * (size_t)N) + 2 * sizeof(int)));
+  char* hi = (char*)ctx->h_in.p;
+  if (n_face) std::memcpy(hi + oAb, Ab, sizeof(double) * 4 * (size_t)n_face);
+  std::memcpy(hi + ox0, x0, sizeof(double) * 9);
+  std::memcpy(hi + oxf, xf, sizeof(double) * 9);
+  std::memcpy(hi + olim, lim, sizeof(double) * 3);
+  {
+    double* hd = (double*)(hi + odt);
+    uint8_t* hs = (uint8_t*)(hi + osig);
+    for (int d = 0; d < n_dt; d++)
+      for (int s = 0; s < n_sigma; s++)
+      {
+        hd[(size_t)d * n_sigma + s] = dts[d];
+        if (P > 0) std::memcpy(hs + ((size_t)d * n_sigma + s) * N, sigmas + (size_t)s * N, N);
+        else std::memset(hs + ((size_t)d * n_sigma + s) * N, 0, N);
+      }
+    int* po = (int*)(hi + opo); po[0] = 0; po[1] = P;
+    int* fo = (int*)(hi + ofo); fo[0] = 0; for (int p = 0; p < P; p++) fo[p + 1] = face_ofs[p + 1];
+    int* co = (int*)(hi + oco); co[0] = 0; co[1] = n_cand;
+  }
+  cudaStream_t st = ctx->stream;
+  char* din = (char*)ctx->d_in.p;
+  char* dout = (char*)ctx->d_out.p;
+  FQ_CUDA(cudaMemcpyAsync(din, hi, in_bytes, cudaMemcpyHostToDevice, st));
+  int rc = launch_solve(ctx, N, force_final, 1, (const double*)(din + ox0), (const double*)(din + oxf),
+                        (const double*)(din + olim), (const int*)(din + opo), (const int*)(din + ofo),
+                        (const double*)(din + oAb), (const int*)(din + oco), n_cand, n_face,
+                        (const double*)(din + odt), (const uint8_t*)(din + osig), (uint8_t*)(dout + ofeas),
+                        (double*)(dout + ocost), (double*)(dout + ocoef), nullptr, st);
+  if (rc) return rc;
+  FqSelectArgs sa;
+  sa.n_dt = n_dt; sa.n_sigma = n_sigma; sa.N = N;
+  sa.feasible = (const uint8_t*)(dout + ofeas); sa.cost = (const double*)(dout + ocost);
+  sa.coeffs = (const double*)(dout + ocoef);
+  sa.out_idx = (int*)(dout + oidx); sa.out_cost = (double*)(dout + owin); sa.out_coeffs = (double*)(dout + owin) + 1;
+  FQ_CUDA(fq_launch_select(sa, st));
+  char* ho = (char*)ctx->h_out.p;
+  const size_t win_bytes = sizeof(double) * (1 + 12 * (size_t)N);
+  FQ_CUDA(cudaMemcpyAsync(ho, dout + owin, win_bytes + 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  FQ_CUDA(cudaStreamSynchronize(st));
+  static_assert(sizeof(double) == 8, "layout");
+  const int* idx = (const int*)(ho + win_bytes);
+  const double* win = (const double*)ho;
+  if (dt_index) *dt_index = idx[0];
+  if (sigma_index) *sigma_index = idx[1];
+  if (idx[0] < 0) { if (cost) *cost = INFINITY; return 0; }
+  if (cost) *cost = win[0];
+  if (coeffs) std::memcpy(coeffs, win + 1, sizeof(double) * 12 * (size_t)N);
+  return 1;
+}

@@ -1,0 +1,51 @@
+// Device-side interface of the batched corridor-QP solver (sm_100a).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define FQ_WARPS_PER_CTA 4
+#define FQ_EPS_DEP 1e-18      // squared sine below which a new normal counts as dependent on the active set
+#define FQ_ZZ_FLOOR 1e-30
+#define FQ_MAX_ITERS 400
+
+struct FqKernelArgs
+{
+  // plan (device copies of FqPlanHost tables)
+  int N, force_final, ne, nz, nw, NY, ld;
+  const double* TZ;      // NY x nz
+  const double* T0;      // NY x (3+ne)
+  const double* FT;      // ne x 3
+  // problems
+  int n_prob;
+  const double* x0;      // n_prob x 9
+  const double* xf;      // n_prob x 9
+  const double* lim;     // n_prob x 3
+  const int* poly_ofs;   // n_prob+1  -> index into face_ofs
+  const int* face_ofs;   // n_poly_total+1 -> row of Ab
+  const double* Ab;      // rows [Ax Ay Az b]
+  int max_faces;         // max total faces of one problem (sizes the shared staging area)
+  // candidates
+  const int* cand_ofs;   // n_prob+1
+  const double* dt;
+  const uint8_t* sigma;  // n_cand x N
+  // outputs
+  uint8_t* feasible;
+  double* cost;
+  double* coeffs;        // n_cand x N x 12 or nullptr
+  int32_t* iters;        // or nullptr
+};
+
+struct FqSelectArgs
+{
+  int n_dt, n_sigma, N;
+  const uint8_t* feasible;
+  const double* cost;
+  const double* coeffs;  // n_dt*n_sigma x N x 12
+  int* out_idx;          // [0] dt index (-1 none), [1] sigma index
+  double* out_cost;      // [0]
+  double* out_coeffs;    // N x 12
+};
+
+size_t fq_solve_smem_bytes(const FqKernelArgs& a);
+cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream);
+cudaError_t fq_launch_select(const FqSelectArgs& a, cudaStream_t stream);

@@ -1,0 +1,117 @@
+/* faster_b200 -- C ABI of the B200-native trajectory-optimisation core.
+ *
+ * This is the drop-in boundary: everything FASTER's SolverGurobi asks of Gurobi (reference
+ * faster/src/solverGurobi.cpp, calls m.addVar/addConstr/addGenConstrIndicator/setObjective/optimize/get at
+ * :80,:119,:226,:246,:283-286,:349-354,:371-377,:397-404,:513-521,:559-581) is replaced by the entry points below.
+ * Plain pointers and sizes only; no C++/torch types; never throws.  All floating point is IEEE double.
+ *
+ * Model solved per candidate (dt, sigma)  [reference lines in brackets]:
+ *   N cubic segments x 3 axes, coefficients x[t][0..11] = ax ay az bx by bz cx cy cz dx dy dz     [:70-84]
+ *   minimise sum_t sum_axis (6 a)^2                                                                 [:113-119]
+ *   s.t. initial state [:359-380], final state (position only if force_final) [:332-357],
+ *        C2 continuity [:499-524], |v|,|a|,|j| boxes at segment starts [:390-407],
+ *        the 4 Bezier control points of segment t inside polytope sigma[t] [:180-291,:833-862].
+ * A candidate is feasible iff that QP has a solution (row tolerance FQ_ROW_TOL); cost is Gurobi's ObjVal.
+ *
+ * Return codes: 0 ok; <0 error (FQ_E_*), message via fq_last_error().  Per-candidate status is written to
+ * `feasible` (1 optimal, 0 infeasible or numerically abandoned -- the reference maps every non-OPTIMAL Gurobi
+ * status to "not solved", solverGurobi.cpp:580-648).
+ */
+#ifndef FASTER_B200_H
+#define FASTER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQ_ABI_VERSION 1
+#define FQ_MAX_N 16               /* segments per trajectory                                  */
+#define FQ_MAX_POLY 32            /* polytopes per corridor problem                           */
+#define FQ_ROW_TOL 1e-8           /* absolute row violation tolerance (m, m/s, m/s^2, m/s^3)  */
+
+#define FQ_E_ARG (-1)
+#define FQ_E_CUDA (-2)
+#define FQ_E_NOMEM (-3)
+#define FQ_E_NOGPU (-4)
+
+typedef struct fq_ctx fq_ctx;     /* opaque: device, stream, plan tables, scratch             */
+
+int fq_abi_version(void);
+
+/* Creates a solver context on CUDA device `device`.  Fails with FQ_E_NOGPU when no usable GPU exists:
+ * there is no CPU fallback.  Replaces `new GRBEnv()` / GRBModel construction (solverGurobi.hpp:154-155). */
+int fq_create(fq_ctx** out, int device);
+void fq_destroy(fq_ctx* ctx);
+const char* fq_last_error(const fq_ctx* ctx);   /* ctx may be NULL: last creation error */
+
+/* One corridor problem, n_cand candidates (dt[i], sigma[i*N .. i*N+N-1]); HOST pointers.
+ * Replaces the per-trial model rebuild + m.optimize() of genNewTraj (solverGurobi.cpp:449-458) for a whole
+ * batch of trials at once.
+ *   x0, xf     9 doubles each: pos(3) vel(3) accel(3)            (setX0/setXf, :298-330)
+ *   lim        v_max, a_max, j_max                               (setBounds, :409-416)
+ *   P          number of polytopes (0 => no corridor rows, sigma ignored, :217)
+ *   face_ofs   P+1 ints; polytope p owns rows face_ofs[p] .. face_ofs[p+1]-1 of Ab
+ *   Ab         rows [Ax Ay Az b], A x <= b                       (setPolytopes, :175-178; polyhedron.h:114-185)
+ *   feasible   n_cand bytes out;  cost n_cand doubles out (+inf when infeasible)
+ *   coeffs     n_cand*N*12 doubles out in the x[t][i] order of solverGurobi.cpp:72, or NULL
+ *   iters      n_cand int32 out (active-set iterations), or NULL                                         */
+int fq_solve_batch(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf, const double* lim,
+                   int P, const int* face_ofs, const double* Ab, int n_cand, const double* dt,
+                   const uint8_t* sigma, uint8_t* feasible, double* cost, double* coeffs, int32_t* iters);
+
+/* n_prob corridor problems in one launch; HOST pointers.  Problem j owns candidates
+ * cand_ofs[j] .. cand_ofs[j+1]-1 and polytopes poly_ofs[j] .. poly_ofs[j+1]-1 (indices into face_ofs, which has
+ * poly_ofs[n_prob]+1 entries).  x0/xf are n_prob*9, lim n_prob*3.  Outputs as fq_solve_batch. */
+int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf,
+                   const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
+                   const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible, double* cost,
+                   double* coeffs, int32_t* iters);
+
+/* Same as fq_solve_multi with every array already resident in DEVICE memory of the context's GPU.  The library
+ * cannot read device arrays on the host, so the caller also passes `max_cand_per_prob` (largest
+ * cand_ofs[j+1]-cand_ofs[j]) and `max_faces_per_prob` (largest number of Ab rows owned by one problem).  Ab must
+ * be 16-byte aligned.  Launches on `stream` (a cudaStream_t; NULL = the context's stream) and returns without
+ * synchronising. */
+int fq_solve_multi_dev(fq_ctx* ctx, int N, int force_final, int n_prob, const double* d_x0, const double* d_xf,
+                       const double* d_lim, const int* d_poly_ofs, const int* d_face_ofs, const double* d_Ab,
+                       const int* d_cand_ofs, int max_cand_per_prob, int max_faces_per_prob, const double* d_dt,
+                       const uint8_t* d_sigma, uint8_t* d_feasible, double* d_cost, double* d_coeffs,
+                       int32_t* d_iters, void* stream);
+
+/* The dt sweep of genNewTraj (solverGurobi.cpp:445-472) as one launch: candidates are the grid
+ * dts[0..n_dt) x sigmas[0..n_sigma); the winner is the FIRST dt (ascending index) that has any feasible sigma,
+ * and within it the minimum-cost sigma (= the MIQP optimum over the supplied assignments).  HOST pointers.
+ * Returns 1 solved / 0 no feasible candidate / <0 error.  Outputs (may be NULL): winning dt index, sigma
+ * index, cost, coefficients N*12. */
+int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf, const double* lim,
+                    int P, const int* face_ofs, const double* Ab, int n_dt, const double* dts, int n_sigma,
+                    const uint8_t* sigmas, int* dt_index, int* sigma_index, double* cost, double* coeffs);
+
+/* ---- host-side helpers (no GPU needed) ------------------------------------------------------------- */
+
+/* getDTInitial (solverGurobi.cpp:659-759), including its float temporaries and MinPositiveElement
+ * (solverGurobi_utils.hpp:19-32). */
+double fq_dt_initial(const double* x0, const double* xf, const double* lim, int N);
+
+/* resetX (solverGurobi.cpp:382-388): number of samples max(2, (int)(N*dt/DC)). */
+int fq_num_samples(int N, double dt, double DC);
+
+/* fillX (solverGurobi.cpp:122-168): out[i*12 .. i*12+11] = pos vel accel jerk at t=(i+1)*DC; the last
+ * sample's vel/accel/jerk are zeroed. */
+void fq_fill_x(int N, const double* coeffs, double dt, double DC, int n_samples, double* out);
+
+/* Number of non-decreasing assignments C(N+P-1, P-1); if out != NULL writes min(count, cap) rows of N bytes in
+ * lexicographic order. */
+long fq_monotone_sigmas(int N, int P, uint8_t* out, long cap);
+
+/* Introspection (tests): copies the per-(N, force_final) plan tables documented in faster_b200/csrc/fq_plan.h.
+ * Returns NY = 6N+1, or 0 if (N, force_final) is unsupported.  TZ: NY*(N-ne), T0: NY*(3+ne), FT: ne*3,
+ * ne = force_final ? 3 : 2.  Any pointer may be NULL. */
+int fq_plan_tables(int N, int force_final, double* TZ, double* T0, double* FT);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,140 @@
+"""numpy mirror of the CUDA kernel's algorithm (faster_b200/csrc/fq_kernels.cu), step for step, on the same plan
+tables.  Test infrastructure: lets the CPU suite check the kernel's mathematics (normalised variables, table rows,
+Householder/Givens updates, ratio test) against the oracle without a GPU.  Not used by the product.
+"""
+import numpy as np
+
+TOL = 1e-8
+EPS_DEP = 1e-18
+ZZ_FLOOR = 1e-30
+MAX_ITERS = 400
+
+
+def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True):
+    """-> (status, cost, coeffs[N,12], iters)."""
+    TZ, T0, FT = tables
+    ne = 3 if force_final else 2
+    nz, NY = N - ne, 6 * N + 1
+    nw = 3 * nz
+    x0 = np.asarray(x0, float)
+    xf = np.asarray(xf, float)
+    inv = np.array([1 / dt, 1 / dt ** 2, 1 / dt ** 3])
+    Yeq = np.zeros((3, NY))
+    for ax in range(3):
+        s0 = np.array([x0[ax], x0[3 + ax] * dt, x0[6 + ax] * dt * dt])
+        tgt = ([xf[ax]] if force_final else []) + [xf[3 + ax] * dt, xf[6 + ax] * dt * dt]
+        rhs = np.array(tgt) - FT @ s0
+        Yeq[ax] = T0[:, :3] @ s0 + T0[:, 3:] @ rhs
+    w = np.zeros(nw)
+    J = np.eye(nw)
+    R = np.zeros((nw, nw))
+    lam = np.zeros(nw)
+    q = 0
+    it = 0
+
+    def Yof(w):
+        return Yeq + (TZ @ w.reshape(3, nz).T).T if nz > 0 else Yeq.copy()
+
+    Y = Yof(w)
+    rows = []                                    # (t, A row, b) per corridor row
+    if len(polys):
+        for t in range(N):
+            A, b = polys[int(sigma[t])]
+            for f in range(len(b)):
+                rows.append((t, np.asarray(A[f], float), float(b[f])))
+    while True:
+        best, desc = TOL, None
+        for typ in range(3):
+            for ax in range(3):
+                for t in range(N):
+                    y = (typ + 1) * N + 1 + t
+                    val = Y[ax, y]
+                    viol = abs(val) * inv[typ] - lim[typ]
+                    if viol > best:
+                        wv = np.zeros(3)
+                        wv[ax] = inv[typ] if val > 0 else -inv[typ]
+                        best, desc = viol, (y, wv, lim[typ])
+        for t, a, b in rows:
+            for y in (t, 4 * N + 1 + t, 5 * N + 1 + t, t + 1):
+                v = a @ Y[:, y] - b
+                if v > best:
+                    best, desc = v, (y, a, b)
+        if desc is None:
+            status = 1
+            break
+        y, wv, h = desc
+        g = np.concatenate([wv[ax] * TZ[y] for ax in range(3)]) if nz > 0 else np.zeros(0)
+        gg = g @ g
+        lam_p = 0.0
+        done = False
+        while True:
+            it += 1
+            if it > MAX_ITERS:
+                status, done = -1, True
+                break
+            viol = wv @ Y[:, y] - h
+            d = J.T @ g
+            zz = d[q:] @ d[q:]
+            z = -J[:, q:] @ d[q:]
+            r = np.linalg.solve(np.triu(R[:q, :q]), d[:q]) if q > 0 else np.zeros(0)
+            dep = zz <= max(EPS_DEP * gg, ZZ_FLOOR)
+            t1, l = np.inf, -1
+            for k in range(q):
+                if r[k] > 0 and lam[k] / r[k] < t1:
+                    t1, l = lam[k] / r[k], k
+            t2 = np.inf if dep else viol / zz
+            if t1 == np.inf and t2 == np.inf:
+                status, done = 0, True
+                break
+            if t2 <= t1:
+                w = w + t2 * z
+                lam[:q] -= t2 * r
+                lam_p += t2
+                dq, nrm = d[q], np.sqrt(zz)
+                sgn = 1.0 if dq >= 0 else -1.0
+                beta = 1.0 / (zz + abs(dq) * nrm)
+                v = d[q:].copy()
+                v[0] += sgn * nrm
+                u = -z + sgn * nrm * J[:, q]
+                J[:, q:] -= beta * np.outer(u, v)
+                R[:q, q] = d[:q]
+                R[q, q] = -sgn * nrm
+                lam[q] = lam_p
+                q += 1
+                Y = Yof(w)
+                break
+            if not dep:
+                w = w + t1 * z
+            lam[:q] -= t1 * r
+            lam_p += t1
+            # drop l
+            R[:q, l:q - 1] = R[:q, l + 1:q]
+            R[:, q - 1] = 0
+            lam[l:q - 1] = lam[l + 1:q]
+            for j in range(l, q - 1):
+                p, s = R[j, j], R[j + 1, j]
+                hh = np.hypot(p, s)
+                c, sn = (p / hh, s / hh) if hh > 0 else (1.0, 0.0)
+                Rj, Rj1 = R[j, j:q - 1].copy(), R[j + 1, j:q - 1].copy()
+                R[j, j:q - 1] = c * Rj + sn * Rj1
+                R[j + 1, j:q - 1] = c * Rj1 - sn * Rj
+                Jj, Jj1 = J[:, j].copy(), J[:, j + 1].copy()
+                J[:, j] = c * Jj + sn * Jj1
+                J[:, j + 1] = c * Jj1 - sn * Jj
+            q -= 1
+            if not dep:
+                Y = Yof(w)
+        if done:
+            break
+    if status != 1:
+        return status, np.inf, None, it
+    U = Y[:, 3 * N + 1:4 * N + 1]
+    cost = float(np.sum(U * U) * inv[2] ** 2)
+    co = np.zeros((N, 12))
+    for t in range(N):
+        for ax in range(3):
+            co[t, ax] = Y[ax, 3 * N + 1 + t] * inv[2] / 6.0
+            co[t, 3 + ax] = Y[ax, 2 * N + 1 + t] * inv[1] / 2.0
+            co[t, 6 + ax] = Y[ax, N + 1 + t] * inv[0]
+            co[t, 9 + ax] = Y[ax, t]
+    return status, cost, co, it

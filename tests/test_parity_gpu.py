@@ -1,0 +1,177 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU restatement, on identical inputs.
+
+Bar (BASELINE.json north_star): feasibility flags identical, cost and coefficients within 1e-4 relative.
+The tolerance asserted here is tighter (1e-7) because both sides solve the same strictly convex QP exactly.
+"""
+import numpy as np
+import pytest
+
+from faster_b200 import capi, corridor as cr
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-7
+
+
+def _compare(feas_g, cost_g, co_g, feas_o, cost_o, co_o, what):
+    assert np.array_equal(feas_g.astype(bool), feas_o.astype(bool)), "%s: feasibility flags differ at %s" % (
+        what, np.nonzero(feas_g.astype(bool) != feas_o.astype(bool))[0][:10])
+    ok = feas_o.astype(bool)
+    if ok.any():
+        rel = np.abs(cost_g[ok] - cost_o[ok]) / np.maximum(1e-9, np.abs(cost_o[ok]))
+        assert rel.max() <= REL, "%s: cost rel err %.3e" % (what, rel.max())
+        if co_g is not None:
+            scale = np.maximum(1.0, np.abs(co_o[ok]).max(axis=(1, 2), keepdims=True))
+            err = (np.abs(co_g[ok] - co_o[ok]) / scale).max()
+            assert err <= 1e-6, "%s: coefficient err %.3e" % (what, err)
+    assert np.all(np.isinf(cost_g[~ok]))
+
+
+def test_demo_corridor_batch(solver, oracle, demo_corridor):
+    fx = demo_corridor
+    N = fx["N"]
+    sig = cr.monotone_sigmas(N, 3)
+    dts = np.repeat(np.array([0.5, 0.6, 0.7, 0.8, 1.0, 1.5]), len(sig))
+    sigs = np.tile(sig, (6, 1))
+    fg, cg, cog, it = solver.solve_batch(N, fx["x0"], fx["xf"], fx["lim"], fx["polys"], dts, sigs, True, True, True)
+    fo, co_, coo = oracle.solve_batch(N, fx["x0"], fx["xf"], fx["lim"], fx["polys"], dts, sigs, True, True, threads=8)
+    assert fo.sum() > 20 and (~fo.astype(bool)).sum() > 20
+    _compare(fg, cg, cog, fo, co_, coo, "demo corridor")
+    assert (it > 0).all()
+
+
+@pytest.mark.parametrize("N,P,ff,profile", [(10, 3, True, "uav"), (10, 4, False, "uav"), (6, 3, True, "uav"),
+                                            (6, 3, False, "uav"), (15, 8, True, "ground"), (4, 2, False, "uav"),
+                                            (16, 5, True, "uav")])
+def test_random_corridors(solver, oracle, N, P, ff, profile):
+    rng = np.random.default_rng(N * 100 + P)
+    sig_all = cr.monotone_sigmas(N, P) if P <= 4 else cr.sample_monotone_sigmas(N, P, 256, rng)
+    for seed in range(3):
+        pb = cr.make_corridor(1000 + seed, P, N, profile, ff)
+        dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N)
+        facs = np.array([1.0, 1.5, 2.0, 3.0, 4.0, 6.0])
+        sig = sig_all[rng.choice(len(sig_all), min(48, len(sig_all)), replace=False)]
+        dts = np.repeat(facs * max(dti, 2 * pb["DC"]), len(sig))
+        sigs = np.tile(sig, (len(facs), 1))
+        fg, cg, cog, _ = solver.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff, True)
+        fo, co_, coo = oracle.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff, True, threads=8)
+        _compare(fg, cg, cog, fo, co_, coo, "N=%d P=%d seed=%d" % (N, P, seed))
+
+
+def test_no_polytopes_and_zero_dof(solver, oracle):
+    """Config 1: N=3 whole has zero degrees of freedom (pure feasibility check); P=0 means no corridor rows."""
+    lim = [5.0, 5.0, 8.0]
+    x0 = np.zeros(9)
+    for N in (3, 5):
+        for scale in (0.5, 2.0, 4.0):
+            xf = np.zeros(9)
+            xf[:3] = scale * np.array([1.0, -0.7, 0.4])
+            dti = capi.dt_initial(x0, xf, lim, N)
+            dts = np.arange(1, 11) * max(dti, 0.02)
+            fg, cg, cog, _ = solver.solve_batch(N, x0, xf, lim, [], dts, None, True, True)
+            fo, co_, coo = oracle.solve_batch(N, x0, xf, lim, [], dts, np.zeros((len(dts), N), np.uint8), True, True)
+            _compare(fg, cg, cog, fo, co_, coo, "P=0 N=%d" % N)
+            assert fg.any() and not fg.all()
+
+
+def test_infeasible_start_state(solver, oracle):
+    """x0 outside its polytope / beyond the velocity box: every candidate must come back infeasible."""
+    pb = cr.make_corridor(7, 3, 10)
+    sig = cr.monotone_sigmas(10, 3)
+    dts = np.full(len(sig), 0.6)
+    x0 = pb["x0"].copy()
+    x0[2] = -3.0                                 # below the ground face
+    fg, cg, _, _ = solver.solve_batch(10, x0, pb["xf"], pb["lim"], pb["polys"], dts, sig)
+    assert not fg.any() and np.all(np.isinf(cg))
+    x0 = pb["x0"].copy()
+    x0[3] = 9.0                                  # |v0| > v_max
+    fg, cg, _, _ = solver.solve_batch(10, x0, pb["xf"], pb["lim"], pb["polys"], dts, sig)
+    assert not fg.any()
+
+
+def test_multi_matches_batches(solver, oracle):
+    """Heterogeneous launch == the same problems solved one by one."""
+    N, P = 10, 3
+    sig = cr.monotone_sigmas(N, P)
+    probs = [cr.make_corridor(50 + k, P, N) for k in range(5)]
+    x0 = np.array([p["x0"] for p in probs]); xf = np.array([p["xf"] for p in probs])
+    lim = np.array([p["lim"] for p in probs])
+    poly_ofs, face_ofs, rows, cand_ofs, dts, sigs = [0], [0], [], [0], [], []
+    for k, p in enumerate(probs):
+        for A, b in p["polys"]:
+            rows.append(np.hstack([A, b[:, None]])); face_ofs.append(face_ofs[-1] + len(b))
+        poly_ofs.append(poly_ofs[-1] + P)
+        dti = capi.dt_initial(p["x0"], p["xf"], p["lim"], N)
+        n = 20 + 7 * k
+        dts.append((1.0 + 0.25 * np.arange(n)) * dti); sigs.append(sig[np.arange(n) % len(sig)])
+        cand_ofs.append(cand_ofs[-1] + n)
+    Ab = np.ascontiguousarray(np.vstack(rows)); dts_all = np.concatenate(dts); sig_all = np.ascontiguousarray(np.vstack(sigs))
+    fg, cg, cog, _ = solver.solve_multi(N, True, np.ascontiguousarray(x0), np.ascontiguousarray(xf),
+                                        np.ascontiguousarray(lim), np.array(poly_ofs, np.int32),
+                                        np.array(face_ofs, np.int32), Ab, np.array(cand_ofs, np.int32), dts_all,
+                                        sig_all, want_coeffs=True)
+    for k, p in enumerate(probs):
+        a, b = cand_ofs[k], cand_ofs[k + 1]
+        fo, co_, coo = oracle.solve_batch(N, p["x0"], p["xf"], p["lim"], p["polys"], dts[k], sigs[k], True, True)
+        _compare(fg[a:b], cg[a:b], cog[a:b], fo, co_, coo, "multi prob %d" % k)
+
+
+def test_gen_new_traj_matches_oracle_sweep(solver, oracle, demo_corridor):
+    """First feasible dt, minimum-cost assignment: same winner as the oracle's sequential sweep with B&B over
+    ALL assignments (the monotone list must contain the MIQP optimum on these corridors)."""
+    cases = [(demo_corridor["N"], demo_corridor["x0"], demo_corridor["xf"], demo_corridor["lim"], demo_corridor["polys"], True)]
+    for seed in range(4):
+        pb = cr.make_corridor(300 + seed, 3, 10)
+        cases.append((10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], True))
+        pb = cr.make_corridor(400 + seed, 4, 10, force_final=False)
+        cases.append((10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], False))
+    for N, x0, xf, lim, polys, ff in cases:
+        sig = cr.monotone_sigmas(N, len(polys))
+        DC = 0.01
+        dti = capi.dt_initial(x0, xf, lim, N)
+        facs = np.arange(1.0, 11.0, 1.0)
+        dts = facs * max(dti, 2 * DC)
+        g = solver.gen_new_traj(N, x0, xf, lim, polys, dts, sig, ff)
+        o = oracle.gen_new_traj(N, x0, xf, lim, polys, DC, 1.0, 10.0, 1.0, None, ff)
+        assert g["solved"] == o["solved"]
+        if o["solved"]:
+            assert facs[g["dt_index"]] == o["factor"] and g["dt_index"] + 1 == o["trials"]
+            assert abs(g["cost"] - o["cost"]) <= REL * max(1.0, o["cost"])
+            assert np.abs(g["coeffs"] - o["coeffs"]).max() <= 1e-6 * max(1.0, np.abs(o["coeffs"]).max())
+
+
+def test_large_batch_properties(solver):
+    """BASELINE config sizes (1024 whole / 8192 safe candidates): size-independent properties.
+    (i) every feasible solution satisfies the model rows when re-evaluated on the host from the returned
+    coefficients; (ii) cost equals sum (6a)^2; (iii) for a fixed sigma feasibility is monotone here: relaxing dt by
+    large factors keeps these rest-to-rest problems feasible; (iv) identical candidates give identical bits."""
+    for (N, P, ff, ndt, nsig) in ((10, 3, True, 16, 64), (10, 4, False, 32, 256)):
+        pb = cr.make_corridor(2024, P, N, force_final=ff)
+        sig = cr.monotone_sigmas(N, P)[:nsig]
+        dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N)
+        dts = np.repeat(np.arange(1, ndt + 1) * max(dti, 0.02), len(sig))
+        sigs = np.tile(sig, (ndt, 1))
+        f1, c1, co, _ = solver.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff, True)
+        f2, c2, _, _ = solver.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff, False)
+        assert np.array_equal(f1, f2) and np.array_equal(c1, c2)
+        ok = f1.astype(bool)
+        assert ok.any()
+        a = co[ok][:, :, 0:3]
+        assert np.allclose(np.sum((6 * a) ** 2, axis=(1, 2)), c1[ok], rtol=1e-9, atol=1e-12)
+        lim = pb["lim"]
+        for i in np.nonzero(ok)[0][::17]:
+            x = co[i]; dt = dts[i]
+            assert np.abs(x[:, 6:9]).max() <= lim[0] + 1e-6 and np.abs(2 * x[:, 3:6]).max() <= lim[1] + 1e-6
+            assert np.abs(6 * x[:, 0:3]).max() <= lim[2] + 1e-6
+            assert np.allclose(x[0, 9:12], pb["x0"][:3]) and np.allclose(x[0, 6:9], pb["x0"][3:6])
+            for t in range(N):
+                A, b = pb["polys"][sigs[i][t]]
+                a_, b_, c_, d_ = x[t, 0:3], x[t, 3:6], x[t, 6:9], x[t, 9:12]
+                cps = [d_, d_ + c_ * dt / 3, d_ + 2 * c_ * dt / 3 + b_ * dt * dt / 3,
+                       a_ * dt ** 3 + b_ * dt ** 2 + c_ * dt + d_]
+                for cp in cps:
+                    assert (A @ cp - b).max() <= 1e-6
+                if t + 1 < N:
+                    assert np.allclose(cps[3], x[t + 1, 9:12], atol=1e-9)
+                    assert np.allclose(3 * a_ * dt ** 2 + 2 * b_ * dt + c_, x[t + 1, 6:9], atol=1e-9)
+                    assert np.allclose(6 * a_ * dt + 2 * b_, 2 * x[t + 1, 3:6], atol=1e-9)
