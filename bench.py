@@ -195,7 +195,12 @@ def main():
                        torch.zeros(n_cand, dtype=torch.int32, device=dev)))
     gathered = torch.zeros(world * 2 * n_cand, dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) stream: its handle is what the C ABI launches on, and the timing events are
+    # recorded on the same stream (handle 0 would mean "the context's own stream" to the ABI)
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step_resident(with_iters=False):
         for w, d, o in zip(works, devt, outs_d):
@@ -225,12 +230,10 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for i in range(args.steps):
         flush.zero_()                                              # L2 flush between timed steps (outside the events)
         ev[i][0].record()
-        kev[i][0].record()
         step_resident()
         ev[i][1].record()
     barrier()
