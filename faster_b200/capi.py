@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfaster_b200.so")
 _lib = None
 
-EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_solve_batch", "fq_solve_multi",
+EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_set_option", "fq_solve_batch", "fq_solve_multi",
            "fq_solve_multi_dev", "fq_gen_new_traj", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
            "fq_monotone_sigmas", "fq_plan_tables"]
 
@@ -40,6 +40,7 @@ def lib():
         L.fq_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.fq_destroy.argtypes = [C.c_void_p]
         L.fq_destroy.restype = None
+        L.fq_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.fq_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.fq_solve_multi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 13
@@ -123,6 +124,9 @@ class Solver:
             self._h = None
 
     __del__ = close
+
+    def set_option(self, key, value):
+        self._check(self._L.fq_set_option(self._h, key.encode(), int(value)))
 
     def _check(self, rc):
         if rc < 0:

@@ -4,6 +4,7 @@
 #include "fq_plan.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -62,7 +63,12 @@ struct fq_ctx
   Arena d_in, d_out;
   PinnedArena h_in, h_out;
   std::string err;
+  bool force_generic = false;
+  int sm_count = 0;
+  int* d_queues = nullptr;   // ring of work-item counters (one per launch in flight)
+  unsigned queue_pos = 0;
 };
+static const int kQueueRing = 64;
 
 namespace
 {
@@ -127,6 +133,8 @@ extern "C" int fq_create(fq_ctx** out, int device)
   ctx->device = device;
   e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_queues, sizeof(int) * kQueueRing);
   if (e != cudaSuccess)
   {
     std::string msg = std::string("cuda init: ") + cudaGetErrorString(e);
@@ -143,8 +151,16 @@ extern "C" void fq_destroy(fq_ctx* ctx)
   cudaSetDevice(ctx->device);
   for (auto& kv : ctx->plans) { cudaFree(kv.second.TZ); cudaFree(kv.second.T0); cudaFree(kv.second.FT); }
   ctx->d_in.release(); ctx->d_out.release(); ctx->h_in.release(); ctx->h_out.release();
+  if (ctx->d_queues) cudaFree(ctx->d_queues);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+extern "C" int fq_set_option(fq_ctx* ctx, const char* key, int value)
+{
+  if (!ctx || !key) return FQ_E_ARG;
+  if (std::string(key) == "force_generic_kernel") { ctx->force_generic = value != 0; return 0; }
+  return fail(ctx, FQ_E_ARG, std::string("unknown option ") + key);
 }
 
 extern "C" const char* fq_last_error(const fq_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -163,11 +179,13 @@ int launch_solve(fq_ctx* ctx, int N, int force_final, int n_prob, const double* 
   FqKernelArgs a;
   fill_plan_args(*pd, &a);
   a.n_prob = n_prob; a.x0 = d_x0; a.xf = d_xf; a.lim = d_lim; a.poly_ofs = d_poly_ofs; a.face_ofs = d_face_ofs;
-  a.Ab = d_Ab; a.max_faces = max_faces > 0 ? max_faces : 1; a.cand_ofs = d_cand_ofs; a.dt = d_dt; a.sigma = d_sigma;
+  a.Ab = d_Ab; a.max_faces = max_faces > 0 ? max_faces : 1; a.item_cap = N * a.max_faces; a.cand_ofs = d_cand_ofs; a.dt = d_dt; a.sigma = d_sigma;
   a.feasible = d_feasible; a.cost = d_cost; a.coeffs = d_coeffs; a.iters = d_iters;
   if (fq_solve_smem_bytes(a) > 227 * 1024)
     return fail(ctx, FQ_E_ARG, "problem too large for shared memory (N / faces per problem)");
-  FQ_CUDA(fq_launch_solve(a, max_cand, stream));
+  static const bool env_generic = std::getenv("FQ_KERNEL") && std::string(std::getenv("FQ_KERNEL")) == "generic";
+  int* queue = ctx->d_queues + (ctx->queue_pos++ % kQueueRing);   // launches in flight never share a counter
+  FQ_CUDA(fq_launch_solve(a, max_cand, stream, queue, ctx->sm_count, env_generic || ctx->force_generic));
   return 0;
 }
 }  // namespace

@@ -438,6 +438,8 @@ __global__ void __launch_bounds__(256) fq_select_kernel(const FqSelectArgs a)
 }
 }  // namespace
 
+#include "fq_kernels_t.cuh"
+
 size_t fq_solve_smem_bytes(const FqKernelArgs& a)
 {
   const int nzp = a.nz > 0 ? a.nz : 1;
@@ -446,9 +448,29 @@ size_t fq_solve_smem_bytes(const FqKernelArgs& a)
   return doubles * sizeof(double) + (36 + W * per_warp_ints()) * sizeof(int);
 }
 
-cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream)
+bool fq_has_specialised(int N, int force_final, int max_faces)
+{
+  return N >= 4 && N <= 16 && max_faces <= 2047 && (force_final ? N >= 4 : N >= 3);
+}
+
+cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream, int* queue, int sm_count,
+                            bool force_generic)
 {
   if (a.n_prob <= 0 || max_cand_per_prob <= 0) return cudaSuccess;
+  if (!force_generic && fq_has_specialised(a.N, a.force_final, a.max_faces))
+  {
+#define FQ_CASE(NN)                                                                                        \
+  case NN:                                                                                                 \
+    return a.force_final ? fqt::launch_t<NN, true>(a, max_cand_per_prob, stream, queue, sm_count)                    \
+                         : fqt::launch_t<NN, false>(a, max_cand_per_prob, stream, queue, sm_count);
+    switch (a.N)
+    {
+      FQ_CASE(4) FQ_CASE(5) FQ_CASE(6) FQ_CASE(7) FQ_CASE(8) FQ_CASE(9) FQ_CASE(10) FQ_CASE(11) FQ_CASE(12)
+      FQ_CASE(13) FQ_CASE(14) FQ_CASE(15) FQ_CASE(16)
+      default: break;
+    }
+#undef FQ_CASE
+  }
   const size_t smem = fq_solve_smem_bytes(a);
   {  // per-device attribute; cheap enough to set on every launch (contexts on several GPUs share this code)
     cudaError_t e = cudaFuncSetAttribute(fq_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

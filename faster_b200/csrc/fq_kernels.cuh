@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 
 #define FQ_WARPS_PER_CTA 4
+#ifndef FQ_MIN_CTAS_PER_SM
+#define FQ_MIN_CTAS_PER_SM 4
+#endif
 #define FQ_EPS_DEP 1e-18      // squared sine below which a new normal counts as dependent on the active set
 #define FQ_ZZ_FLOOR 1e-30
 #define FQ_MAX_ITERS 400
@@ -24,6 +27,7 @@ struct FqKernelArgs
   const int* face_ofs;   // n_poly_total+1 -> row of Ab
   const double* Ab;      // rows [Ax Ay Az b]
   int max_faces;         // max total faces of one problem (sizes the shared staging area)
+  int item_cap;          // corridor rows per candidate the item list must hold: N * max_faces
   // candidates
   const int* cand_ofs;   // n_prob+1
   const double* dt;
@@ -47,5 +51,10 @@ struct FqSelectArgs
 };
 
 size_t fq_solve_smem_bytes(const FqKernelArgs& a);
-cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream);
+// picks the size-specialised kernel when one exists (4 <= N <= 16, faces <= 2047), else the generic one;
+// force_generic selects the generic kernel regardless (differential testing)
+// `queue` is one int of device memory owned by the caller's context (work-item counter of the persistent kernel)
+cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream, int* queue, int sm_count,
+                            bool force_generic = false);
+bool fq_has_specialised(int N, int force_final, int max_faces);
 cudaError_t fq_launch_select(const FqSelectArgs& a, cudaStream_t stream);

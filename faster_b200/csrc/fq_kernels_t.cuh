@@ -1,0 +1,669 @@
+// Size-specialised solver kernel (compile-time N and whole/safe mode).  Same algorithm and same numerics policy as
+// the generic kernel in fq_kernels.cu (dual active-set on the normalised, equality-eliminated QP of fq_plan.h);
+// what changes is where things live and how the warp's lanes are used:
+//   * sizes are template constants: no integer division, bounded loops unroll, vectors live in registers;
+//   * every lane OWNS fixed rows of Y (row y = lane + 32 r, all three axes): the plan's constant part Yeq stays in
+//     registers, Y = Yeq + TZ w costs one broadcast read of w per column, and the |v|,|a|,|j| box rows
+//     (solverGurobi.cpp:390-407) are checked by the owning lane while the value is still in a register;
+//   * corridor rows (solverGurobi.cpp:249-287) are scanned through a per-candidate item list (segment, face), 32 rows
+//     per pass, one fmax tree per item; the control point that is shared with the previous segment is skipped when
+//     both segments use the same polytope;
+//   * duals, the triangular solve and the ratio test are register/shuffle based (element k of an NW-vector lives in
+//     lane k%32, slot k/32);  reciprocals and square roots use the MUFU seed + Newton steps instead of IEEE division;
+//   * a CTA owns a chunk of candidates of ONE problem (polytope rows staged once); its warps pull candidates from a
+//     shared counter so a slow candidate does not idle the other warps.
+#pragma once
+
+namespace fqt
+{
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int W = FQ_WARPS_PER_CTA;
+constexpr int CHUNK = 32;          // candidates per CTA
+constexpr unsigned BOX_FLAG = 0x40000000u;
+
+template <int N_, bool WHOLE_>
+struct Dims
+{
+  static constexpr int N = N_;
+  static constexpr int NE = WHOLE_ ? 3 : 2;
+  static constexpr int NZ = N_ - NE;
+  static constexpr int NW = 3 * NZ;
+  static constexpr int NY = 6 * N_ + 1;
+  static constexpr int NYP = NY | 1;             // odd row stride of Y per axis
+  static constexpr int LD = NW | 1;              // odd leading dimension of J and R
+  static constexpr int TZLD = NZ | 1;            // odd row stride of TZ in shared memory
+  static constexpr int SLOTS = (NW + 31) / 32;   // elements of an NW-vector per lane
+  static constexpr int RPL = (NY + 31) / 32;     // Y rows per lane
+  static constexpr int PER_WARP_DOUBLES = 2 * NW * LD + 3 * NYP + 2 * NW + 2;
+};
+// per-warp bytes: solver state + item list (item_cap 16-bit entries)
+template <class D>
+__host__ __device__ inline int per_warp_bytes(int item_cap) { return D::PER_WARP_DOUBLES * 8 + ((item_cap * 2 + 15) & ~15); }
+
+__device__ __forceinline__ double fast_rcp(double x)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double hx = 0.5 * x;
+  r = fma(fma(-hx * r, r, 0.5), r, r);
+  r = fma(fma(-hx * r, r, 0.5), r, r);
+  r = fma(fma(-hx * r, r, 0.5), r, r);
+  return r;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+template <class D>
+struct WarpState
+{
+  double* J;            // NW x LD row-major
+  double* R;            // column-major: R(j,k) at R[k*LD + j]
+  double* Y;            // 3 x NYP
+  double* w;            // NW
+  double* d;            // NW
+  unsigned short* items;
+};
+
+// Ranking key of a row: hi word of (violation - tol) * S[y] as a signed int, S[y] = 1/|TZ[y]| (distance of the
+// iterate to the row's hyperplane in w-space, for unit face normals).  Positive iff the row is violated; ordering
+// positive doubles by their hi word keeps 20 mantissa bits, plenty for choosing the entering row.
+__device__ __forceinline__ int rank_key(double u) { return __double2hiint(u); }
+
+// Y = Yeq + TZ w for the lane's rows, box rows checked on the fly.  Updates the lane's best (key, code).
+// bthr[r] = (limit + tol) * dt^k for box rows (huge for other rows), srow[r] = S[y].
+template <class D>
+__device__ __forceinline__ void update_Y(const WarpState<D>& m, const double* __restrict__ TZ,
+                                         const double (&Yeq)[D::RPL][3], const double (&bthr)[D::RPL],
+                                         const double (&srow)[D::RPL], int lane, int& bkey, unsigned& bcode)
+{
+  double acc[D::RPL][3];
+#pragma unroll
+  for (int r = 0; r < D::RPL; r++)
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) acc[r][ax] = Yeq[r][ax];
+#pragma unroll
+  for (int k = 0; k < D::NZ; k++)
+  {
+    const double w0 = m.w[k], w1 = m.w[D::NZ + k], w2 = m.w[2 * D::NZ + k];
+#pragma unroll
+    for (int r = 0; r < D::RPL; r++)
+    {
+      const int y = lane + 32 * r;
+      if (y < D::NY)
+      {
+        const double t = TZ[y * D::TZLD + k];
+        acc[r][0] = fma(t, w0, acc[r][0]);
+        acc[r][1] = fma(t, w1, acc[r][1]);
+        acc[r][2] = fma(t, w2, acc[r][2]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < D::RPL; r++)
+  {
+    const int y = lane + 32 * r;
+    if (y < D::NY)
+    {
+#pragma unroll
+      for (int ax = 0; ax < 3; ax++)
+      {
+        m.Y[ax * D::NYP + y] = acc[r][ax];
+        const int key = rank_key((fabs(acc[r][ax]) - bthr[r]) * srow[r]);
+        if (key > bkey) { bkey = key; bcode = BOX_FLAG | (unsigned)(ax << 8) | (unsigned)y; }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// remove active element l (0 <= l < q); lam / rdinv are per-lane register slots
+template <class D>
+__device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l, int q, double (&lam)[D::SLOTS],
+                                         double (&rdinv)[D::SLOTS])
+{
+  constexpr int LD = D::LD;
+  // R: columns l+1..q-1 move left (each lane moves its own rows)
+#pragma unroll
+  for (int s = 0; s < D::SLOTS; s++)
+  {
+    const int j = lane + 32 * s;
+    if (j < q)
+      for (int k = l; k < q - 1; k++) m.R[k * LD + j] = m.R[(k + 1) * LD + j];
+  }
+  // lam: element k <- element k+1 for k in [l, q-1)
+  {
+    double nxt[D::SLOTS];
+#pragma unroll
+    for (int s = 0; s < D::SLOTS; s++)
+    {
+      const double same = __shfl_sync(FULL, lam[s], (lane + 1) & 31);
+      const double wrap = (s + 1 < D::SLOTS) ? __shfl_sync(FULL, lam[(s + 1 < D::SLOTS) ? s + 1 : s], 0) : 0.0;
+      nxt[s] = lane == 31 ? wrap : same;
+    }
+#pragma unroll
+    for (int s = 0; s < D::SLOTS; s++)
+    {
+      const int k = lane + 32 * s;
+      if (k >= l && k < q - 1) lam[s] = nxt[s];
+    }
+  }
+  __syncwarp();
+  for (int j = l; j < q - 1; j++)
+  {
+    const double p = m.R[j * LD + j], sb = m.R[j * LD + j + 1];
+    const double h2 = fma(p, p, sb * sb);
+    double c = 1.0, sn = 0.0, hi = 0.0;
+    if (h2 > 0) { hi = fast_rsqrt(h2); c = p * hi; sn = sb * hi; }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < D::SLOTS; s++)
+    {
+      const int k = lane + 32 * s;
+      if (k >= j && k < q - 1)
+      { // rows j, j+1 of R at column k
+        const double u = m.R[k * LD + j], v = m.R[k * LD + j + 1];
+        m.R[k * LD + j] = fma(c, u, sn * v);
+        m.R[k * LD + j + 1] = fma(c, v, -sn * u);
+      }
+      if (k == j) rdinv[s] = hi;                 // new diagonal is h = sqrt(h2)
+      if (k < D::NW)
+      { // columns j, j+1 of J at row k
+        const double u = m.J[k * LD + j], v = m.J[k * LD + j + 1];
+        m.J[k * LD + j] = fma(c, u, sn * v);
+        m.J[k * LD + j + 1] = fma(c, v, -sn * u);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <class D>
+__device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict__ TZ, const double* __restrict__ TZN,
+                                const double* __restrict__ SY, const double* __restrict__ sAb,
+                                const int* __restrict__ sfo, const WarpState<D>& m, int* __restrict__ seg_ofs,
+                                int prob, int cand, int lane, const double (&btype)[D::RPL],
+                                const double (&srow)[D::RPL])
+{
+  constexpr int N = D::N, NZ = D::NZ, NW = D::NW, NY = D::NY, NYP = D::NYP, LD = D::LD, NE = D::NE, SLOTS = D::SLOTS;
+  const double dt = a.dt[cand], dt2 = dt * dt;
+  const double inv1 = 1.0 / dt, inv2 = inv1 * inv1, inv3 = inv2 * inv1;
+  const double lim0 = a.lim[prob * 3 + 0], lim1 = a.lim[prob * 3 + 1], lim2 = a.lim[prob * 3 + 2];
+  const int P = a.poly_ofs[prob + 1] - a.poly_ofs[prob];
+
+  // ---- per-lane constants of the owned rows: Yeq, box scale and limit
+  double Yeq[D::RPL][3], bthr[D::RPL];
+  {
+    double hdr[3][3 + NE];
+    const double* x0 = a.x0 + prob * 9;
+    const double* xf = a.xf + prob * 9;
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++)
+    {
+      const double s0 = x0[ax], s1 = x0[3 + ax] * dt, s2 = x0[6 + ax] * dt2;
+      hdr[ax][0] = s0; hdr[ax][1] = s1; hdr[ax][2] = s2;
+      double tgt[3];
+      int e = 0;
+      if (NE == 3) tgt[e++] = xf[ax];
+      tgt[e++] = xf[3 + ax] * dt;
+      tgt[e++] = xf[6 + ax] * dt2;
+#pragma unroll
+      for (int k = 0; k < NE; k++)
+        hdr[ax][3 + k] = tgt[k] - fma(a.FT[k * 3 + 0], s0, fma(a.FT[k * 3 + 1], s1, a.FT[k * 3 + 2] * s2));
+    }
+#pragma unroll
+    for (int r = 0; r < D::RPL; r++)
+    {
+      const int y = lane + 32 * r;
+      const double ty = btype[r];                // 0 none, 1 v, 2 a, 3 j
+      bthr[r] = ty == 1.0 ? (lim0 + FQ_ROW_TOL) * dt : (ty == 2.0 ? (lim1 + FQ_ROW_TOL) * dt2
+                                                                    : (ty == 3.0 ? (lim2 + FQ_ROW_TOL) * dt2 * dt : 1e300));
+#pragma unroll
+      for (int ax = 0; ax < 3; ax++) Yeq[r][ax] = 0.0;
+      if (y < NY)
+      {
+        const double* t0 = a.T0 + y * (3 + NE);
+#pragma unroll
+        for (int k = 0; k < 3 + NE; k++)
+        {
+          const double t = __ldg(t0 + k);
+#pragma unroll
+          for (int ax = 0; ax < 3; ax++) Yeq[r][ax] = fma(t, hdr[ax][k], Yeq[r][ax]);
+        }
+      }
+    }
+  }
+  // ---- corridor item list: item = t << 12 | need_cp0 << 11 | face (row of the staged Ab)
+  int total_rows = 0;
+  if (P > 0)
+  {
+    int F = 0, p = 0, pprev = -1;
+    if (lane < N)
+    {
+      p = a.sigma[(size_t)cand * N + lane];
+      if (p >= P) p = P - 1;
+      F = sfo[p + 1] - sfo[p];
+    }
+    pprev = __shfl_up_sync(FULL, p, 1);
+    const int need0 = (lane == 0 || pprev != p) ? 1 : 0;
+    int incl = F;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    total_rows = __shfl_sync(FULL, incl, N - 1);
+    // seg_ofs[t] = first item of segment t; seg_ofs[16 + t] = (need_cp0 << 11) | first staged face of sigma[t]
+    if (lane < N) { seg_ofs[lane] = incl - F; seg_ofs[16 + lane] = (need0 << 11) | sfo[p]; }
+    else if (lane < 16) seg_ofs[lane] = 0x7fffffff;
+    __syncwarp();
+    // a.item_cap >= N * (faces of the problem) >= total_rows by construction (host side)
+    for (int i = lane; i < total_rows; i += 32)
+    {
+      int t = 0;                                   // largest t with seg_ofs[t] <= i  (N <= 16: 4 halving steps)
+#pragma unroll
+      for (int step = 8; step; step >>= 1)
+        if (seg_ofs[t + step] <= i) t += step;
+      const int meta = seg_ofs[16 + t];
+      m.items[i] = (unsigned short)((t << 12) | (meta + (i - seg_ofs[t])));
+    }
+  }
+  // ---- J = I, w = 0
+  for (int idx = lane; idx < NW * LD; idx += 32) m.J[idx] = 0.0;
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < SLOTS; s++)
+  {
+    const int j = lane + 32 * s;
+    if (j < NW) { m.J[j * LD + j] = 1.0; m.w[j] = 0.0; }
+  }
+  __syncwarp();
+
+  double lam[SLOTS], rdinv[SLOTS], r[SLOTS], z[SLOTS], dreg[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; s++) { lam[s] = 0; rdinv[s] = 0; r[s] = 0; z[s] = 0; dreg[s] = 0; }
+  int q = 0, status = -2, it = 0;
+  int bkey = 0;
+  unsigned bcode = 0;
+  update_Y<D>(m, TZ, Yeq, bthr, srow, lane, bkey, bcode);
+  while (status == -2)
+  {
+    // ================= most violated corridor row (box rows were checked by update_Y) =================
+    for (int i = lane; i < total_rows; i += 32)
+    {
+      const unsigned item = m.items[i];
+      const int t = item >> 12, gf = item & 0x7ff;
+      const double2 a01 = *reinterpret_cast<const double2*>(sAb + 4 * gf);
+      const double2 a23 = *reinterpret_cast<const double2*>(sAb + 4 * gf + 2);     // a23.y = b + tol
+      const double* Y0 = m.Y; const double* Y1 = m.Y + NYP; const double* Y2 = m.Y + 2 * NYP;
+      const int y1 = 4 * N + 1 + t, y2 = 5 * N + 1 + t;
+      const double u1 = fma(a01.x, Y0[y1], fma(a01.y, Y1[y1], fma(a23.x, Y2[y1], -a23.y))) * SY[y1];
+      const double u2 = fma(a01.x, Y0[y2], fma(a01.y, Y1[y2], fma(a23.x, Y2[y2], -a23.y))) * SY[y2];
+      const double u3 = fma(a01.x, Y0[t + 1], fma(a01.y, Y1[t + 1], fma(a23.x, Y2[t + 1], -a23.y))) * SY[t + 1];
+      int km = max(max(rank_key(u1), rank_key(u2)), rank_key(u3));
+      if (item & 0x800u)
+        km = max(km, rank_key(fma(a01.x, Y0[t], fma(a01.y, Y1[t], fma(a23.x, Y2[t], -a23.y))) * SY[t]));
+      if (km > bkey) { bkey = km; bcode = (unsigned)i; }
+    }
+    const int mk = __reduce_max_sync(FULL, bkey);
+    if (mk <= 0) { status = 1; break; }
+    const int key = bkey;
+    const int src = __ffs(__ballot_sync(FULL, key == mk)) - 1;
+    const unsigned code = __shfl_sync(FULL, bcode, src);
+    // ---- decode the chosen row: Y row y, weights (w0,w1,w2), right-hand side h
+    int y;
+    double w0 = 0, w1 = 0, w2 = 0, h;
+    if (code & BOX_FLAG)
+    {
+      y = code & 0xff;
+      const int ax = (code >> 8) & 3;
+      const double val = m.Y[ax * NYP + y];
+      const double sinv = y <= 2 * N ? inv1 : (y <= 3 * N ? inv2 : inv3);
+      h = y <= 2 * N ? lim0 : (y <= 3 * N ? lim1 : lim2);
+      const double s = val > 0 ? sinv : -sinv;
+      w0 = ax == 0 ? s : 0.0; w1 = ax == 1 ? s : 0.0; w2 = ax == 2 ? s : 0.0;
+    }
+    else
+    {
+      const unsigned item = m.items[code];
+      const int t = item >> 12, gf = item & 0x7ff;
+      w0 = sAb[4 * gf]; w1 = sAb[4 * gf + 1]; w2 = sAb[4 * gf + 2];
+      const double hb = sAb[4 * gf + 3];            // b + tol
+      h = hb - FQ_ROW_TOL;
+      const int ys[4] = { 4 * N + 1 + t, 5 * N + 1 + t, t + 1, t };
+      y = ys[0];
+      int best = -0x7fffffff;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+      {
+        if (k == 3 && !(item & 0x800u)) break;
+        const int kk = rank_key(fma(w0, m.Y[ys[k]], fma(w1, m.Y[NYP + ys[k]], fma(w2, m.Y[2 * NYP + ys[k]], -hb))) * SY[ys[k]]);
+        if (kk > best) { best = kk; y = ys[k]; }
+      }
+    }
+    const double gg = (w0 * w0 + w1 * w1 + w2 * w2) * TZN[y];
+    double lam_p = 0;
+    for (;;)
+    {
+      if (++it > FQ_MAX_ITERS) { status = -1; break; }
+      const double viol = fma(w0, m.Y[y], fma(w1, m.Y[NYP + y], fma(w2, m.Y[2 * NYP + y], -h)));
+      // ---- d = J' g with g = (w0, w1, w2) (x) TZ[y];  zz = |d2|^2
+      double zzp = 0;
+      {
+        double s0[SLOTS], s1[SLOTS], s2[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++) { s0[s] = 0; s1[s] = 0; s2[s] = 0; }
+#pragma unroll
+        for (int k = 0; k < NZ; k++)
+        {
+          const double tk = TZ[y * D::TZLD + k];
+#pragma unroll
+          for (int s = 0; s < SLOTS; s++)
+          {
+            const int j = lane + 32 * s;
+            if (j < NW)
+            {
+              s0[s] = fma(tk, m.J[k * LD + j], s0[s]);
+              s1[s] = fma(tk, m.J[(NZ + k) * LD + j], s1[s]);
+              s2[s] = fma(tk, m.J[(2 * NZ + k) * LD + j], s2[s]);
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++)
+        {
+          const int j = lane + 32 * s;
+          dreg[s] = fma(w0, s0[s], fma(w1, s1[s], w2 * s2[s]));
+          if (j < NW)
+          {
+            m.d[j] = dreg[s];
+            if (j >= q) zzp = fma(dreg[s], dreg[s], zzp);
+          }
+        }
+      }
+      const double zz = warp_sum(zzp);
+      __syncwarp();
+      // ---- z = -J2 d2 (lane-owned rows)
+#pragma unroll
+      for (int s = 0; s < SLOTS; s++)
+      {
+        const int i = lane + 32 * s;
+        double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+        if (i < NW)
+        {
+          const double* Ji = m.J + i * LD;
+          int j = q;
+          for (; j + 3 < NW; j += 4)
+          {
+            acc0 = fma(Ji[j], m.d[j], acc0);
+            acc1 = fma(Ji[j + 1], m.d[j + 1], acc1);
+            acc2 = fma(Ji[j + 2], m.d[j + 2], acc2);
+            acc3 = fma(Ji[j + 3], m.d[j + 3], acc3);
+          }
+          for (; j < NW; j++) acc0 = fma(Ji[j], m.d[j], acc0);
+        }
+        z[s] = -((acc0 + acc1) + (acc2 + acc3));
+      }
+      // ---- r = R^-1 d1 (registers + shuffles)
+#pragma unroll
+      for (int s = 0; s < SLOTS; s++) r[s] = dreg[s];
+      for (int k = q - 1; k >= 0; k--)
+      {
+        const int ks = k >> 5;
+        double rk = (SLOTS > 1 && ks == 1) ? r[SLOTS - 1] * rdinv[SLOTS - 1] : r[0] * rdinv[0];
+        rk = __shfl_sync(FULL, rk, k & 31);
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++)
+        {
+          const int j = lane + 32 * s;
+          if (j < k) r[s] = fma(-m.R[k * LD + j], rk, r[s]);
+          else if (j == k) r[s] = rk;
+        }
+      }
+      const bool dep = zz <= fmax(FQ_EPS_DEP * gg, FQ_ZZ_FLOOR);
+      // ---- dual ratio test
+      double best = INFINITY;
+      int bk = -1;
+#pragma unroll
+      for (int s = 0; s < SLOTS; s++)
+      {
+        const int k = lane + 32 * s;
+        if (k < q && r[s] > 0)
+        {
+          const double ratio = lam[s] * fast_rcp(r[s]);
+          if (ratio < best) { best = ratio; bk = k; }
+        }
+      }
+      const double t1 = warp_min(best);
+      int l = -1;
+      if (t1 < INFINITY)
+      {
+        const int s2 = __ffs(__ballot_sync(FULL, best == t1)) - 1;
+        l = __shfl_sync(FULL, bk, s2);
+      }
+      const double t2 = dep ? INFINITY : viol * fast_rcp(zz);
+      if (t1 == INFINITY && t2 == INFINITY) { status = 0; break; }
+      if (t2 <= t1)
+      { // ---- full step: the row becomes active
+        const double rn = fast_rsqrt(zz), nrm = zz * rn;
+        const double dq = m.d[q], sgn = dq >= 0 ? 1.0 : -1.0;
+        const double beta = fast_rcp(fma(fabs(dq), nrm, zz)), vq = fma(sgn, nrm, dq);
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++)
+        {
+          const int i = lane + 32 * s;
+          if (i < NW)
+          {
+            m.w[i] = fma(t2, z[s], m.w[i]);
+            double* Ji = m.J + i * LD;
+            const double bu = beta * fma(sgn * nrm, Ji[q], -z[s]);
+            Ji[q] = fma(-bu, vq, Ji[q]);
+#pragma unroll 4
+            for (int j = q + 1; j < NW; j++) Ji[j] = fma(-bu, m.d[j], Ji[j]);
+          }
+          if (i < q) { lam[s] = fma(-t2, r[s], lam[s]); m.R[q * LD + i] = dreg[s]; }
+          if (i == q) { lam[s] = lam_p + t2; rdinv[s] = -sgn * rn; m.R[q * LD + q] = -sgn * nrm; }
+        }
+        q++;
+        __syncwarp();
+        bkey = 0; bcode = 0;
+        update_Y<D>(m, TZ, Yeq, bthr, srow, lane, bkey, bcode);
+        break;
+      }
+      // ---- partial step: active element l leaves
+#pragma unroll
+      for (int s = 0; s < SLOTS; s++)
+      {
+        const int i = lane + 32 * s;
+        if (!dep && i < NW) m.w[i] = fma(t1, z[s], m.w[i]);
+        if (i < q) lam[s] = fma(-t1, r[s], lam[s]);
+      }
+      lam_p += t1;
+      __syncwarp();
+      drop_row<D>(m, lane, l, q, lam, rdinv);
+      q--;
+      if (!dep)
+      {
+        int dummy_k = 0;
+        unsigned dummy_c = 0;
+        update_Y<D>(m, TZ, Yeq, bthr, srow, lane, dummy_k, dummy_c);
+      }
+    }
+  }
+
+  // ================= outputs =================
+  double cp = 0;
+  if (status == 1)
+    for (int i = lane; i < 3 * N; i += 32)
+    {
+      const int ax = i / N, t = i - ax * N;
+      const double u = m.Y[ax * NYP + 3 * N + 1 + t];
+      cp = fma(u, u, cp);
+    }
+  const double cost = warp_sum(cp) * (inv3 * inv3);
+  if (lane == 0)
+  {
+    a.feasible[cand] = status == 1;
+    a.cost[cand] = status == 1 ? cost : INFINITY;
+    if (a.iters) a.iters[cand] = status == -1 ? -it : it;
+  }
+  if (a.coeffs)
+  {
+    double* out = a.coeffs + (size_t)cand * N * 12;
+    for (int idx = lane; idx < 12 * N; idx += 32)
+    {
+      const int t = idx / 12, c = idx - 12 * t, kind = c / 3, ax = c - 3 * kind;
+      const double* Ya = m.Y + ax * NYP;
+      double v;
+      if (kind == 0) v = Ya[3 * N + 1 + t] * inv3 * (1.0 / 6.0);
+      else if (kind == 1) v = Ya[2 * N + 1 + t] * inv2 * 0.5;
+      else if (kind == 2) v = Ya[N + 1 + t] * inv1;
+      else v = Ya[t];
+      out[idx] = status == 1 ? v : 0.0;
+    }
+  }
+  __syncwarp();
+}
+
+// Persistent CTAs: each CTA repeatedly takes a work item (problem, chunk of CHUNK candidates) from a global counter,
+// stages that problem's polytope rows, and its warps pull candidates of the chunk from a shared counter.
+template <int N_, bool WHOLE_>
+__global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <= 15 ? 3 : 2))) fq_solve_kernel_t(const FqKernelArgs a, int chunks_per_prob,
+                                                                                int n_items, int* __restrict__ queue)
+{
+  using D = Dims<N_, WHOLE_>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_next, s_item;
+
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  double* sAb = sm;            sm += 4 * a.max_faces;
+  double* TZ = sm;             sm += D::NY * D::TZLD;
+  double* TZN = sm;            sm += D::NY;
+  double* SY = sm;             sm += D::NY;
+  unsigned char* wraw = reinterpret_cast<unsigned char*>(sm);
+  const int pwb = per_warp_bytes<D>(a.item_cap);
+  int* sfo = reinterpret_cast<int*>(wraw + (size_t)W * pwb);
+
+  // ---- plan tables: once per CTA
+  for (int i = threadIdx.x; i < D::NY * D::NZ; i += blockDim.x)
+  {
+    const int y = i / D::NZ, k = i - y * D::NZ;
+    TZ[y * D::TZLD + k] = a.TZ[i];
+  }
+  for (int y = threadIdx.x; y < D::NY; y += blockDim.x)
+  {
+    double s = 0;
+    for (int k = 0; k < D::NZ; k++) { const double t = a.TZ[y * D::NZ + k]; s = fma(t, t, s); }
+    TZN[y] = s;
+    SY[y] = s > 1e-30 ? rsqrt(s) : 1e15;       // constant rows: any violation outranks everything (=> infeasible)
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpState<D> m;
+  int* seg_ofs;
+  {
+    double* p = reinterpret_cast<double*>(wraw + (size_t)warp * pwb);
+    m.J = p;   p += D::NW * D::LD;
+    m.R = p;   p += D::NW * D::LD;
+    m.Y = p;   p += 3 * D::NYP;
+    m.w = p;   p += D::NW;
+    m.d = p;   p += D::NW + 2;
+    m.items = reinterpret_cast<unsigned short*>(p);
+    seg_ofs = sfo + 40 + warp * 32;
+  }
+  // box type of the lane's rows: 1 v (rows N+1..2N), 2 a (2N+1..3N), 3 j (3N+1..4N), 0 otherwise
+  double btype[D::RPL], srow[D::RPL];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < D::RPL; r++)
+  {
+    const int y = lane + 32 * r;
+    btype[r] = (y >= N_ + 1 && y <= 2 * N_) ? 1.0 : ((y >= 2 * N_ + 1 && y <= 3 * N_) ? 2.0 : ((y >= 3 * N_ + 1 && y <= 4 * N_) ? 3.0 : 0.0));
+    srow[r] = y < D::NY ? SY[y] : 0.0;
+  }
+  for (;;)
+  {
+    __syncthreads();                               // everyone is done with the previous item's staged rows
+    if (threadIdx.x == 0) { s_item = atomicAdd(queue, 1); s_next = 0; }
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) break;
+    const int prob = item / chunks_per_prob, chunk = item - prob * chunks_per_prob;
+    const int c_begin = a.cand_ofs[prob], c_end = a.cand_ofs[prob + 1];
+    const int first = c_begin + chunk * CHUNK;
+    if (first >= c_end) continue;
+    const int count = min(CHUNK, c_end - first);
+    const int p0 = a.poly_ofs[prob], P = a.poly_ofs[prob + 1] - p0;
+    const int f0 = a.face_ofs[p0];
+    const int nf = P > 0 ? a.face_ofs[p0 + P] - f0 : 0;
+    {
+      const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
+      double2* dst = reinterpret_cast<double2*>(sAb);
+      for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x)
+      {
+        double2 v = src[i];
+        if (i & 1) v.y += FQ_ROW_TOL;              // rows are staged as [Ax Ay Az b+tol]
+        dst[i] = v;
+      }
+      for (int i = threadIdx.x; i <= P && i < 36; i += blockDim.x) sfo[i] = a.face_ofs[p0 + i] - f0;
+    }
+    __syncthreads();
+    for (;;)
+    {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&s_next, 1);
+      c = __shfl_sync(FULL, c, 0);
+      if (c >= count) break;
+      solve_candidate<D>(a, TZ, TZN, SY, sAb, sfo, m, seg_ofs, prob, first + c, lane, btype, srow);
+    }
+  }
+}
+
+template <int N_, bool WHOLE_>
+size_t smem_bytes_t(int max_faces, int item_cap)
+{
+  using D = Dims<N_, WHOLE_>;
+  return (size_t)8 * (4 * max_faces + D::NY * D::TZLD + 2 * D::NY) + (size_t)W * per_warp_bytes<D>(item_cap) +
+         (40 + W * 32) * 4 + 16;
+}
+
+template <int N_, bool WHOLE_>
+cudaError_t launch_t(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream, int* queue, int sm_count)
+{
+  const size_t smem = smem_bytes_t<N_, WHOLE_>(a.max_faces, a.item_cap);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  auto kern = fq_solve_kernel_t<N_, WHOLE_>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const int chunks = (max_cand_per_prob + CHUNK - 1) / CHUNK;
+  const long long n_items = (long long)chunks * a.n_prob;
+  if (n_items > 0x7fffffffLL) return cudaErrorInvalidValue;
+  long long grid = (long long)per_sm * sm_count;
+  if (grid > n_items) grid = n_items;
+  e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)grid, W * 32, smem, stream>>>(a, chunks, (int)n_items, queue);
+  return cudaGetLastError();
+}
+}  // namespace fqt

@@ -46,6 +46,10 @@ int fq_create(fq_ctx** out, int device);
 void fq_destroy(fq_ctx* ctx);
 const char* fq_last_error(const fq_ctx* ctx);   /* ctx may be NULL: last creation error */
 
+/* Tuning / testing knobs.  "force_generic_kernel" (0/1): use the size-generic kernel even where a size-specialised one
+ * exists (the two are independent implementations of the same solve; tests run both).  Returns 0 or FQ_E_ARG. */
+int fq_set_option(fq_ctx* ctx, const char* key, int value);
+
 /* One corridor problem, n_cand candidates (dt[i], sigma[i*N .. i*N+N-1]); HOST pointers.
  * Replaces the per-trial model rebuild + m.optimize() of genNewTraj (solverGurobi.cpp:449-458) for a whole
  * batch of trials at once.

@@ -10,8 +10,9 @@ ZZ_FLOOR = 1e-30
 MAX_ITERS = 400
 
 
-def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True):
-    """-> (status, cost, coeffs[N,12], iters)."""
+def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised=False):
+    """-> (status, cost, coeffs[N,12], iters).  normalised=False mirrors the size-generic kernel (entering row = largest
+    violation); normalised=True mirrors the size-specialised kernel (largest (violation - tol) / |TZ[y]|)."""
     TZ, T0, FT = tables
     ne = 3 if force_final else 2
     nz, NY = N - ne, 6 * N + 1
@@ -42,23 +43,29 @@ def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True):
             A, b = polys[int(sigma[t])]
             for f in range(len(b)):
                 rows.append((t, np.asarray(A[f], float), float(b[f])))
+    TZN = np.sum(TZ * TZ, axis=1) if nz > 0 else np.zeros(NY)
+    SY = np.where(TZN > 1e-30, 1.0 / np.sqrt(np.maximum(TZN, 1e-300)), 1e15)
+
+    def rank(viol, y, scale=1.0):
+        return (viol - TOL) * SY[y] / scale if normalised else viol - TOL
+
     while True:
-        best, desc = TOL, None
+        best, desc = 0.0, None
         for typ in range(3):
             for ax in range(3):
                 for t in range(N):
                     y = (typ + 1) * N + 1 + t
                     val = Y[ax, y]
                     viol = abs(val) * inv[typ] - lim[typ]
-                    if viol > best:
+                    if rank(viol, y, inv[typ]) > best:
                         wv = np.zeros(3)
                         wv[ax] = inv[typ] if val > 0 else -inv[typ]
-                        best, desc = viol, (y, wv, lim[typ])
+                        best, desc = rank(viol, y, inv[typ]), (y, wv, lim[typ])
         for t, a, b in rows:
             for y in (t, 4 * N + 1 + t, 5 * N + 1 + t, t + 1):
                 v = a @ Y[:, y] - b
-                if v > best:
-                    best, desc = v, (y, a, b)
+                if rank(v, y) > best:
+                    best, desc = rank(v, y), (y, a, b)
         if desc is None:
             status = 1
             break

@@ -175,3 +175,25 @@ def test_large_batch_properties(solver):
                     assert np.allclose(cps[3], x[t + 1, 9:12], atol=1e-9)
                     assert np.allclose(3 * a_ * dt ** 2 + 2 * b_ * dt + c_, x[t + 1, 6:9], atol=1e-9)
                     assert np.allclose(6 * a_ * dt + 2 * b_, 2 * x[t + 1, 3:6], atol=1e-9)
+
+
+@pytest.mark.parametrize("N,P,ff", [(10, 3, True), (10, 4, False), (6, 3, True), (15, 8, False), (16, 4, True), (4, 2, True)])
+def test_generic_and_specialised_kernels_agree(built_lib, N, P, ff):
+    """Two independent CUDA implementations of the same solve (size-generic / size-specialised) on the same batch."""
+    rng = np.random.default_rng(N + 31 * P)
+    s = capi.Solver(0)
+    try:
+        sig_all = cr.monotone_sigmas(N, P) if P <= 4 and N <= 10 else cr.sample_monotone_sigmas(N, P, 300, rng)
+        pb = cr.make_corridor(4242 + N, P, N, "uav" if N != 15 else "ground", ff)
+        dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N)
+        facs = np.linspace(1.0, 6.0, 11)
+        sig = sig_all[rng.choice(len(sig_all), min(100, len(sig_all)), replace=False)]
+        dts = np.repeat(facs * max(dti, 0.02), len(sig))
+        sigs = np.tile(sig, (len(facs), 1))
+        fa, ca, coa, ita = s.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff, True, True)
+        s.set_option("force_generic_kernel", 1)
+        fb, cb, cob, itb = s.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff, True, True)
+        _compare(fa, ca, coa, fb, cb, cob, "specialised vs generic N=%d" % N)
+        assert ita.max() > 0 and np.abs(ita.astype(int) - itb).max() <= 4
+    finally:
+        s.close()

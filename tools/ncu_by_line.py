@@ -34,7 +34,7 @@ for f in sorted(os.listdir(tmp)):
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
-            cur = int(m.group(2))
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             insts.append((cur, ln.split("*/", 1)[1].strip().rstrip(";")))
@@ -59,11 +59,21 @@ for (line, sass), r in zip(lines_of, body):
     for k in range(4):
         agg[line][k] += v[k]
         tot[k] += v[k]
-src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "faster_b200", "csrc", "fq_kernels.cu")).read().splitlines()
+_srcs = {}
+def srcline(key):
+    if not key:
+        return "?"
+    f, n = key
+    if f not in _srcs:
+        try:
+            _srcs[f] = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "faster_b200", "csrc", f)).read().splitlines()
+        except Exception:
+            _srcs[f] = []
+    L = _srcs[f]
+    return "%s:%d %s" % (f.replace("fq_kernels", "k"), n, L[n - 1].strip()[:80] if n <= len(L) else "?")
 print("total warp-inst %d  stall samples %d  smem wavefronts %d (excess %d)" % (tot[0], tot[1], tot[3], tot[2]))
 for key, name in ((0, "instructions executed"), (1, "stall samples")):
     print("---- top lines by", name)
     for line, v in sorted(agg.items(), key=lambda kv: -kv[1][key])[:top]:
-        s = src[line - 1].strip()[:90] if line and line <= len(src) else "?"
-        print("%5s inst %5.1f%% stall %5.1f%% smem-excess %5.1f%% | %s" % (line, 100.0 * v[0] / tot[0], 100.0 * v[1] / max(1, tot[1]),
-                                                              100.0 * v[2] / max(1, tot[2]), s))
+        print("inst %5.1f%% stall %5.1f%% smem-excess %5.1f%% | %s" % (100.0 * v[0] / tot[0], 100.0 * v[1] / max(1, tot[1]),
+                                                              100.0 * v[2] / max(1, tot[2]), srcline(line)))
