@@ -58,7 +58,8 @@ def make_workload(n_corr, seed0, kind):
              poly_ofs=np.array(poly_ofs, np.int32), face_ofs=np.array(face_ofs, np.int32),
              Ab=np.ascontiguousarray(np.vstack(rows)), cand_ofs=(np.arange(n_corr + 1) * CAND).astype(np.int32),
              dt=dts.reshape(-1), sigma=sigs.reshape(-1, N_SEG), probs=probs,
-             max_faces=int(max(face_ofs[poly_ofs[j + 1]] - face_ofs[poly_ofs[j]] for j in range(n_corr))))
+             max_faces=int(max(face_ofs[poly_ofs[j + 1]] - face_ofs[poly_ofs[j]] for j in range(n_corr))),
+             max_poly_faces=int(np.diff(face_ofs).max()))
     return w
 
 
@@ -201,6 +202,9 @@ def main():
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
+
+    # hint for the device-pointer API (the host-pointer API derives it itself): sizes the per-warp row list
+    solver.set_option("max_faces_per_polytope", max(w["max_poly_faces"] for w in works))
 
     def step_resident(with_iters=False):
         for w, d, o in zip(works, devt, outs_d):

@@ -3,6 +3,7 @@
 #include "fq_kernels.cuh"
 #include "fq_plan.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -65,10 +66,12 @@ struct fq_ctx
   std::string err;
   bool force_generic = false;
   int sm_count = 0;
-  int* d_queues = nullptr;   // ring of work-item counters (one per launch in flight)
-  unsigned queue_pos = 0;
+  int* d_counters = nullptr;      // ring of per-problem claim counters (one slot per launch in flight)
+  int counters_cap = 0;           // problems per slot
+  unsigned counters_pos = 0;
+  int max_poly_faces_hint = 0;    // option "max_faces_per_polytope" (device-pointer API only)
 };
-static const int kQueueRing = 64;
+static const int kCounterSlots = 16;
 
 namespace
 {
@@ -134,7 +137,8 @@ extern "C" int fq_create(fq_ctx** out, int device)
   e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_queues, sizeof(int) * kQueueRing);
+  ctx->counters_cap = 4096;
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counters, sizeof(int) * (size_t)kCounterSlots * ctx->counters_cap);
   if (e != cudaSuccess)
   {
     std::string msg = std::string("cuda init: ") + cudaGetErrorString(e);
@@ -151,7 +155,7 @@ extern "C" void fq_destroy(fq_ctx* ctx)
   cudaSetDevice(ctx->device);
   for (auto& kv : ctx->plans) { cudaFree(kv.second.TZ); cudaFree(kv.second.T0); cudaFree(kv.second.FT); }
   ctx->d_in.release(); ctx->d_out.release(); ctx->h_in.release(); ctx->h_out.release();
-  if (ctx->d_queues) cudaFree(ctx->d_queues);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -160,6 +164,7 @@ extern "C" int fq_set_option(fq_ctx* ctx, const char* key, int value)
 {
   if (!ctx || !key) return FQ_E_ARG;
   if (std::string(key) == "force_generic_kernel") { ctx->force_generic = value != 0; return 0; }
+  if (std::string(key) == "max_faces_per_polytope") { ctx->max_poly_faces_hint = value > 0 ? value : 0; return 0; }
   return fail(ctx, FQ_E_ARG, std::string("unknown option ") + key);
 }
 
@@ -170,8 +175,9 @@ namespace
 // common launch: every pointer is a device pointer
 int launch_solve(fq_ctx* ctx, int N, int force_final, int n_prob, const double* d_x0, const double* d_xf,
                  const double* d_lim, const int* d_poly_ofs, const int* d_face_ofs, const double* d_Ab,
-                 const int* d_cand_ofs, int max_cand, int max_faces, const double* d_dt, const uint8_t* d_sigma,
-                 uint8_t* d_feasible, double* d_cost, double* d_coeffs, int32_t* d_iters, cudaStream_t stream)
+                 const int* d_cand_ofs, int max_cand, int max_faces, int max_poly_faces, const double* d_dt,
+                 const uint8_t* d_sigma, uint8_t* d_feasible, double* d_cost, double* d_coeffs, int32_t* d_iters,
+                 cudaStream_t stream)
 {
   PlanDev* pd = nullptr;
   int rc = get_plan(ctx, N, force_final, &pd);
@@ -179,13 +185,22 @@ int launch_solve(fq_ctx* ctx, int N, int force_final, int n_prob, const double* 
   FqKernelArgs a;
   fill_plan_args(*pd, &a);
   a.n_prob = n_prob; a.x0 = d_x0; a.xf = d_xf; a.lim = d_lim; a.poly_ofs = d_poly_ofs; a.face_ofs = d_face_ofs;
-  a.Ab = d_Ab; a.max_faces = max_faces > 0 ? max_faces : 1; a.item_cap = N * a.max_faces; a.cand_ofs = d_cand_ofs; a.dt = d_dt; a.sigma = d_sigma;
+  a.Ab = d_Ab; a.max_faces = max_faces > 0 ? max_faces : 1;
+  a.item_cap = N * (max_poly_faces > 0 && max_poly_faces <= a.max_faces ? max_poly_faces : a.max_faces); a.cand_ofs = d_cand_ofs; a.dt = d_dt; a.sigma = d_sigma;
   a.feasible = d_feasible; a.cost = d_cost; a.coeffs = d_coeffs; a.iters = d_iters;
   if (fq_solve_smem_bytes(a) > 227 * 1024)
     return fail(ctx, FQ_E_ARG, "problem too large for shared memory (N / faces per problem)");
   static const bool env_generic = std::getenv("FQ_KERNEL") && std::string(std::getenv("FQ_KERNEL")) == "generic";
-  int* queue = ctx->d_queues + (ctx->queue_pos++ % kQueueRing);   // launches in flight never share a counter
-  FQ_CUDA(fq_launch_solve(a, max_cand, stream, queue, ctx->sm_count, env_generic || ctx->force_generic));
+  if (n_prob > ctx->counters_cap)
+  { // rare: grow the counter ring (needs the device idle because earlier launches may still use the old one)
+    FQ_CUDA(cudaDeviceSynchronize());
+    cudaFree(ctx->d_counters);
+    ctx->d_counters = nullptr;
+    ctx->counters_cap = n_prob + n_prob / 2;
+    FQ_CUDA(cudaMalloc(&ctx->d_counters, sizeof(int) * (size_t)kCounterSlots * ctx->counters_cap));
+  }
+  int* counters = ctx->d_counters + (size_t)(ctx->counters_pos++ % kCounterSlots) * ctx->counters_cap;
+  FQ_CUDA(fq_launch_solve(a, max_cand, stream, counters, ctx->sm_count, env_generic || ctx->force_generic));
   return 0;
 }
 }  // namespace
@@ -203,8 +218,8 @@ extern "C" int fq_solve_multi_dev(fq_ctx* ctx, int N, int force_final, int n_pro
   if (((uintptr_t)d_Ab & 15) != 0) return fail(ctx, FQ_E_ARG, "Ab must be 16-byte aligned");
   FQ_CUDA(cudaSetDevice(ctx->device));
   return launch_solve(ctx, N, force_final, n_prob, d_x0, d_xf, d_lim, d_poly_ofs, d_face_ofs, d_Ab, d_cand_ofs,
-                      max_cand_per_prob, max_faces_per_prob, d_dt, d_sigma, d_feasible, d_cost, d_coeffs, d_iters,
-                      stream ? (cudaStream_t)stream : ctx->stream);
+                      max_cand_per_prob, max_faces_per_prob, ctx->max_poly_faces_hint, d_dt, d_sigma, d_feasible, d_cost,
+                      d_coeffs, d_iters, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
 namespace
@@ -218,13 +233,13 @@ struct HostLayout
 // validates the host description and computes sizes
 int describe(fq_ctx* ctx, int N, int force_final, int n_prob, const int* poly_ofs, const int* face_ofs,
              const int* cand_ofs, const uint8_t* sigma, bool want_coeffs, bool want_iters, HostLayout* L,
-             int* n_cand, int* n_poly, int* n_face, int* max_cand, int* max_faces)
+             int* n_cand, int* n_poly, int* n_face, int* max_cand, int* max_faces, int* max_poly_faces)
 {
   const int ne = force_final ? 3 : 2;
   if (N < ne || N > FQ_MAX_N) return fail(ctx, FQ_E_ARG, "N out of range");
   if (n_prob <= 0) return fail(ctx, FQ_E_ARG, "n_prob <= 0");
   if (poly_ofs[0] != 0 || cand_ofs[0] != 0 || face_ofs[0] != 0) return fail(ctx, FQ_E_ARG, "offset arrays must start at 0");
-  *max_cand = 0; *max_faces = 0;
+  *max_cand = 0; *max_faces = 0; *max_poly_faces = 0;
   for (int j = 0; j < n_prob; j++)
   {
     const int P = poly_ofs[j + 1] - poly_ofs[j], nc = cand_ofs[j + 1] - cand_ofs[j];
@@ -233,7 +248,10 @@ int describe(fq_ctx* ctx, int N, int force_final, int n_prob, const int* poly_of
     const int nf = face_ofs[poly_ofs[j + 1]] - face_ofs[poly_ofs[j]];
     if (nf < 0) return fail(ctx, FQ_E_ARG, "face_ofs not monotone");
     for (int p = poly_ofs[j]; p < poly_ofs[j + 1]; p++)
+    {
       if (face_ofs[p + 1] < face_ofs[p]) return fail(ctx, FQ_E_ARG, "face_ofs not monotone");
+      if (face_ofs[p + 1] - face_ofs[p] > *max_poly_faces) *max_poly_faces = face_ofs[p + 1] - face_ofs[p];
+    }
     if (P > 0 && sigma)
       for (size_t i = (size_t)cand_ofs[j] * N; i < (size_t)cand_ofs[j + 1] * N; i++)
         if (sigma[i] >= P) return fail(ctx, FQ_E_ARG, "sigma entry >= number of polytopes");
@@ -273,9 +291,9 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
   if (!x0 || !xf || !lim || !poly_ofs || !face_ofs || !cand_ofs || !dt || !feasible || !cost)
     return fail(ctx, FQ_E_ARG, "NULL argument");
   HostLayout L;
-  int n_cand, n_poly, n_face, max_cand, max_faces;
+  int n_cand, n_poly, n_face, max_cand, max_faces, max_poly_faces;
   int rc = describe(ctx, N, force_final, n_prob, poly_ofs, face_ofs, cand_ofs, sigma, coeffs != nullptr,
-                    iters != nullptr, &L, &n_cand, &n_poly, &n_face, &max_cand, &max_faces);
+                    iters != nullptr, &L, &n_cand, &n_poly, &n_face, &max_cand, &max_faces, &max_poly_faces);
   if (rc) return rc;
   if (n_cand == 0) return 0;
   if (n_poly > 0 && (!Ab || !sigma)) return fail(ctx, FQ_E_ARG, "polytopes given but Ab or sigma is NULL");
@@ -309,7 +327,7 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
   if (n_poly == 0) FQ_CUDA(cudaMemsetAsync(din + L.sigma, 0, sig_bytes, st));
   rc = launch_solve(ctx, N, force_final, n_prob, (const double*)(din + L.x0), (const double*)(din + L.xf),
                     (const double*)(din + L.lim), (const int*)(din + L.poly_ofs), (const int*)(din + L.face_ofs),
-                    (const double*)(din + L.Ab), (const int*)(din + L.cand_ofs), max_cand, max_faces,
+                    (const double*)(din + L.Ab), (const int*)(din + L.cand_ofs), max_cand, max_faces, max_poly_faces,
                     (const double*)(din + L.dt), (const uint8_t*)(din + L.sigma), (uint8_t*)(dout + L.feasible),
                     (double*)(dout + L.cost), coeffs ? (double*)(dout + L.coeffs) : nullptr,
                     iters ? (int32_t*)(dout + L.iters) : nullptr, st);
@@ -367,6 +385,8 @@ extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double
   if (n_cand_ll > (1LL << 30)) return fail(ctx, FQ_E_ARG, "too many candidates");
   const int n_cand = (int)n_cand_ll;
   const int n_face = P > 0 ? face_ofs[P] : 0;
+  int max_pf = 0;
+  for (int p = 0; p < P; p++) max_pf = std::max(max_pf, face_ofs[p + 1] - face_ofs[p]);
   if (P > 0)
     for (size_t i = 0; i < (size_t)n_sigma * N; i++)
       if (sigmas[i] >= P) return fail(ctx, FQ_E_ARG, "sigma entry >= number of polytopes");
@@ -419,7 +439,7 @@ extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double
   FQ_CUDA(cudaMemcpyAsync(din, hi, in_bytes, cudaMemcpyHostToDevice, st));
   int rc = launch_solve(ctx, N, force_final, 1, (const double*)(din + ox0), (const double*)(din + oxf),
                         (const double*)(din + olim), (const int*)(din + opo), (const int*)(din + ofo),
-                        (const double*)(din + oAb), (const int*)(din + oco), n_cand, n_face,
+                        (const double*)(din + oAb), (const int*)(din + oco), n_cand, n_face, max_pf,
                         (const double*)(din + odt), (const uint8_t*)(din + osig), (uint8_t*)(dout + ofeas),
                         (double*)(dout + ocost), (double*)(dout + ocoef), nullptr, st);
   if (rc) return rc;

@@ -453,16 +453,17 @@ bool fq_has_specialised(int N, int force_final, int max_faces)
   return N >= 4 && N <= 16 && max_faces <= 2047 && (force_final ? N >= 4 : N >= 3);
 }
 
-cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream, int* queue, int sm_count,
+cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream, int* counters, int sm_count,
                             bool force_generic)
 {
   if (a.n_prob <= 0 || max_cand_per_prob <= 0) return cudaSuccess;
   if (!force_generic && fq_has_specialised(a.N, a.force_final, a.max_faces))
   {
+    const long long total_hint = (long long)max_cand_per_prob * a.n_prob;
 #define FQ_CASE(NN)                                                                                        \
   case NN:                                                                                                 \
-    return a.force_final ? fqt::launch_t<NN, true>(a, max_cand_per_prob, stream, queue, sm_count)                    \
-                         : fqt::launch_t<NN, false>(a, max_cand_per_prob, stream, queue, sm_count);
+    return a.force_final ? fqt::launch_t<NN, true>(a, total_hint, stream, counters, sm_count)                        \
+                         : fqt::launch_t<NN, false>(a, total_hint, stream, counters, sm_count);
     switch (a.N)
     {
       FQ_CASE(4) FQ_CASE(5) FQ_CASE(6) FQ_CASE(7) FQ_CASE(8) FQ_CASE(9) FQ_CASE(10) FQ_CASE(11) FQ_CASE(12)

@@ -53,8 +53,9 @@ struct FqSelectArgs
 size_t fq_solve_smem_bytes(const FqKernelArgs& a);
 // picks the size-specialised kernel when one exists (4 <= N <= 16, faces <= 2047), else the generic one;
 // force_generic selects the generic kernel regardless (differential testing)
-// `queue` is one int of device memory owned by the caller's context (work-item counter of the persistent kernel)
-cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream, int* queue, int sm_count,
+// `counters`: a.n_prob ints of device memory owned by the caller's context (per-problem claim counters of the
+// persistent kernel; zeroed by the launch on `stream`)
+cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream, int* counters, int sm_count,
                             bool force_generic = false);
 bool fq_has_specialised(int N, int force_final, int max_faces);
 cudaError_t fq_launch_select(const FqSelectArgs& a, cudaStream_t stream);

@@ -196,7 +196,7 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
 }
 
 template <class D>
-__device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict__ TZ, const double* __restrict__ TZN,
+__device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict__ TZ,
                                 const double* __restrict__ SY, const double* __restrict__ sAb,
                                 const int* __restrict__ sfo, const WarpState<D>& m, int* __restrict__ seg_ofs,
                                 int prob, int cand, int lane, const double (&btype)[D::RPL],
@@ -359,7 +359,8 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
         if (kk > best) { best = kk; y = ys[k]; }
       }
     }
-    const double gg = (w0 * w0 + w1 * w1 + w2 * w2) * TZN[y];
+    const double sy = SY[y];
+    const double gg = (w0 * w0 + w1 * w1 + w2 * w2) * fast_rcp(sy * sy);   // |g|^2 = |w|^2 |TZ[y]|^2
     double lam_p = 0;
     for (;;)
     {
@@ -543,20 +544,22 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
   __syncwarp();
 }
 
-// Persistent CTAs: each CTA repeatedly takes a work item (problem, chunk of CHUNK candidates) from a global counter,
-// stages that problem's polytope rows, and its warps pull candidates of the chunk from a shared counter.
+// Persistent CTAs.  counters[j] = next unclaimed candidate of problem j (zeroed before the launch).  A CTA adopts a
+// problem that still has unclaimed candidates (scanning from a CTA-specific start so CTAs spread over the problems),
+// stages its polytope rows once, and its warps claim candidates one by one with a global atomic until the problem is
+// drained; several CTAs may drain the same problem.  Block-wide barriers happen only when a CTA changes problem, and
+// at the end of the launch every warp finishes within one candidate of the others.
 template <int N_, bool WHOLE_>
-__global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <= 15 ? 3 : 2))) fq_solve_kernel_t(const FqKernelArgs a, int chunks_per_prob,
-                                                                                int n_items, int* __restrict__ queue)
+__global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <= 15 ? 3 : 2)))
+    fq_solve_kernel_t(const FqKernelArgs a, int* __restrict__ counters)
 {
   using D = Dims<N_, WHOLE_>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_next, s_item;
+  __shared__ int s_prob;
 
   double* sm = reinterpret_cast<double*>(smem_raw);
   double* sAb = sm;            sm += 4 * a.max_faces;
   double* TZ = sm;             sm += D::NY * D::TZLD;
-  double* TZN = sm;            sm += D::NY;
   double* SY = sm;             sm += D::NY;
   unsigned char* wraw = reinterpret_cast<unsigned char*>(sm);
   const int pwb = per_warp_bytes<D>(a.item_cap);
@@ -572,7 +575,6 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <
   {
     double s = 0;
     for (int k = 0; k < D::NZ; k++) { const double t = a.TZ[y * D::NZ + k]; s = fma(t, t, s); }
-    TZN[y] = s;
     SY[y] = s > 1e-30 ? rsqrt(s) : 1e15;       // constant rows: any violation outranks everything (=> infeasible)
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -588,28 +590,42 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <
     m.items = reinterpret_cast<unsigned short*>(p);
     seg_ofs = sfo + 40 + warp * 32;
   }
-  // box type of the lane's rows: 1 v (rows N+1..2N), 2 a (2N+1..3N), 3 j (3N+1..4N), 0 otherwise
   double btype[D::RPL], srow[D::RPL];
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < D::RPL; r++)
-  {
+  { // box type of the lane's rows: 1 v (rows N+1..2N), 2 a (2N+1..3N), 3 j (3N+1..4N), 0 otherwise
     const int y = lane + 32 * r;
     btype[r] = (y >= N_ + 1 && y <= 2 * N_) ? 1.0 : ((y >= 2 * N_ + 1 && y <= 3 * N_) ? 2.0 : ((y >= 3 * N_ + 1 && y <= 4 * N_) ? 3.0 : 0.0));
     srow[r] = y < D::NY ? SY[y] : 0.0;
   }
+  const int n_prob = a.n_prob;
+  int cursor = (int)(((long long)blockIdx.x * n_prob) / gridDim.x);   // CTA-specific starting problem
+  int visited = 0;
   for (;;)
   {
-    __syncthreads();                               // everyone is done with the previous item's staged rows
-    if (threadIdx.x == 0) { s_item = atomicAdd(queue, 1); s_next = 0; }
+    // ---- adopt the next problem (cyclically from `cursor`) that still has unclaimed candidates
+    if (warp == 0)
+    {
+      int found = -1;
+      while (visited < n_prob && found < 0)
+      {
+        const int j = visited + lane;
+        int pj = cursor + j;
+        if (pj >= n_prob) pj -= n_prob;
+        bool open = false;
+        if (j < n_prob)
+          open = *reinterpret_cast<volatile int*>(counters + pj) < a.cand_ofs[pj + 1] - a.cand_ofs[pj];
+        const unsigned bal = __ballot_sync(FULL, open);
+        if (bal) { const int first = __ffs(bal) - 1; found = cursor + visited + first; visited += first + 1; }
+        else visited += 32;
+      }
+      if (lane == 0) s_prob = found < 0 ? -1 : (found >= n_prob ? found - n_prob : found);
+    }
     __syncthreads();
-    const int item = s_item;
-    if (item >= n_items) break;
-    const int prob = item / chunks_per_prob, chunk = item - prob * chunks_per_prob;
-    const int c_begin = a.cand_ofs[prob], c_end = a.cand_ofs[prob + 1];
-    const int first = c_begin + chunk * CHUNK;
-    if (first >= c_end) continue;
-    const int count = min(CHUNK, c_end - first);
+    const int prob = s_prob;
+    if (prob < 0) break;
+    const int c_begin = a.cand_ofs[prob], count = a.cand_ofs[prob + 1] - c_begin;
     const int p0 = a.poly_ofs[prob], P = a.poly_ofs[prob + 1] - p0;
     const int f0 = a.face_ofs[p0];
     const int nf = P > 0 ? a.face_ofs[p0 + P] - f0 : 0;
@@ -628,11 +644,12 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <
     for (;;)
     {
       int c = 0;
-      if (lane == 0) c = atomicAdd(&s_next, 1);
+      if (lane == 0) c = atomicAdd(counters + prob, 1);
       c = __shfl_sync(FULL, c, 0);
       if (c >= count) break;
-      solve_candidate<D>(a, TZ, TZN, SY, sAb, sfo, m, seg_ofs, prob, first + c, lane, btype, srow);
+      solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, c_begin + c, lane, btype, srow);
     }
+    __syncthreads();                               // everyone is done with the staged rows
   }
 }
 
@@ -640,12 +657,13 @@ template <int N_, bool WHOLE_>
 size_t smem_bytes_t(int max_faces, int item_cap)
 {
   using D = Dims<N_, WHOLE_>;
-  return (size_t)8 * (4 * max_faces + D::NY * D::TZLD + 2 * D::NY) + (size_t)W * per_warp_bytes<D>(item_cap) +
+  return (size_t)8 * (4 * max_faces + D::NY * D::TZLD + D::NY) + (size_t)W * per_warp_bytes<D>(item_cap) +
          (40 + W * 32) * 4 + 16;
 }
 
+// `counters`: a.n_prob ints of device memory, zeroed here on `stream`
 template <int N_, bool WHOLE_>
-cudaError_t launch_t(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream, int* queue, int sm_count)
+cudaError_t launch_t(const FqKernelArgs& a, long long total_cand_hint, cudaStream_t stream, int* counters, int sm_count)
 {
   const size_t smem = smem_bytes_t<N_, WHOLE_>(a.max_faces, a.item_cap);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
@@ -656,14 +674,13 @@ cudaError_t launch_t(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t 
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  const int chunks = (max_cand_per_prob + CHUNK - 1) / CHUNK;
-  const long long n_items = (long long)chunks * a.n_prob;
-  if (n_items > 0x7fffffffLL) return cudaErrorInvalidValue;
   long long grid = (long long)per_sm * sm_count;
-  if (grid > n_items) grid = n_items;
-  e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  const long long need = (total_cand_hint + W - 1) / W;      // no point in more CTAs than candidates / warps
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  e = cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)a.n_prob, stream);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)grid, W * 32, smem, stream>>>(a, chunks, (int)n_items, queue);
+  kern<<<(unsigned)grid, W * 32, smem, stream>>>(a, counters);
   return cudaGetLastError();
 }
 }  // namespace fqt
