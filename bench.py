@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((float(f[0]), float(f[1]), f[2:]))
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def summary(self):
         if not self.samples:
@@ -156,7 +156,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--corridors", type=int, default=64, help="corridor problems per GPU per step")
@@ -194,7 +194,7 @@ def main():
         outs_h.append((torch.zeros(n_cand, dtype=torch.uint8).pin_memory(), torch.zeros(n_cand, dtype=torch.float64).pin_memory()))
         outs_d.append((torch.zeros(n_cand, dtype=torch.uint8, device=dev), torch.zeros(n_cand, dtype=torch.float64, device=dev),
                        torch.zeros(n_cand, dtype=torch.int32, device=dev)))
-    gathered = torch.zeros(world * 2 * n_cand, dtype=torch.float64, device=dev) if world > 1 else None
+    from faster_b200 import shard
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     # a dedicated (non-default) stream: its handle is what the C ABI launches on, and the timing events are
     # recorded on the same stream (handle 0 would mean "the context's own stream" to the ABI)
@@ -213,8 +213,8 @@ def main():
                                    d["Ab"].data_ptr(), d["cand_ofs"].data_ptr(), CAND, w["max_faces"],
                                    d["dt"].data_ptr(), d["sigma"].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), 0,
                                    o[2].data_ptr() if with_iters else 0, stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, torch.cat([outs_d[0][1], outs_d[1][1]]))
+        if world > 1:   # the path's one exchange: all-gather of the per-candidate costs (+inf = infeasible)
+            shard.all_gather_costs(torch.cat([outs_d[0][1], outs_d[1][1]]), world * C, 2 * CAND)
 
     def step_e2e():
         for w, h, o in zip(works, host, outs_h):
