@@ -192,9 +192,11 @@ def main():
         host.append(h)
         devt.append({k: v.to(dev) for k, v in h.items()})
         outs_h.append((torch.zeros(n_cand, dtype=torch.uint8).pin_memory(), torch.zeros(n_cand, dtype=torch.float64).pin_memory()))
-        outs_d.append((torch.zeros(n_cand, dtype=torch.uint8, device=dev), torch.zeros(n_cand, dtype=torch.float64, device=dev),
+        outs_d.append((torch.zeros(n_cand, dtype=torch.uint8, device=dev), None,
                        torch.zeros(n_cand, dtype=torch.int32, device=dev)))
     from faster_b200 import shard
+    cost_all = torch.zeros(2 * n_cand, dtype=torch.float64, device=dev)       # [whole costs | safe costs]
+    outs_d = [(o[0], cost_all[k * n_cand:(k + 1) * n_cand], o[2]) for k, o in enumerate(outs_d)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     # a dedicated (non-default) stream: its handle is what the C ABI launches on, and the timing events are
     # recorded on the same stream (handle 0 would mean "the context's own stream" to the ABI)
@@ -214,7 +216,7 @@ def main():
                                    d["dt"].data_ptr(), d["sigma"].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), 0,
                                    o[2].data_ptr() if with_iters else 0, stream)
         if world > 1:   # the path's one exchange: all-gather of the per-candidate costs (+inf = infeasible)
-            shard.all_gather_costs(torch.cat([outs_d[0][1], outs_d[1][1]]), world * C, 2 * CAND)
+            shard.all_gather_costs(cost_all, world * C, 2 * CAND)
 
     def step_e2e():
         for w, h, o in zip(works, host, outs_h):
@@ -277,6 +279,20 @@ def main():
     feas_frac = float(torch.cat([outs_d[0][0], outs_d[1][0]]).double().mean())
     same = all(bool(torch.equal(outs_d[k][0].cpu(), outs_h[k][0])) for k in range(2))
 
+    # single-replan latency: one genNewTraj sweep (10 factors x all 66 monotone assignments) through the C ABI,
+    # host buffers in, winner's coefficients out -- what the robot experiences against its 10 ms budget
+    from faster_b200 import corridor as cr
+    pb = works[0]["probs"][0]
+    sig66 = cr.monotone_sigmas(N_SEG, 3)
+    dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N_SEG)
+    dts10 = np.arange(1.0, 11.0) * max(dti, 2 * pb["DC"])
+    lat = []
+    for i in range(60):
+        t0 = time.perf_counter()
+        g = solver.gen_new_traj(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts10, sig66, True)
+        lat.append(time.perf_counter() - t0)
+    replan_us = float(np.median(lat[10:]) * 1e6)
+
     t = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -305,6 +321,7 @@ def main():
                            "e2e_matches_resident": same},
                 "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": 2 * args.steps,
+                "replan_latency_us": {"value": replan_us, "what": "fq_gen_new_traj: 10 factors x 66 assignments, N=10, P=3, host in/out, median of 50"},
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "kernel": "fq_solve_kernel", "kernel_ms": kernel_ms,

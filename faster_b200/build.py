@@ -24,17 +24,18 @@ def _stale():
         os.path.getmtime(os.path.abspath(__file__)) > t
 
 
-def build(force=False, verbose=False):
-    if not (force or _stale()):
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """extra_flags/out: build an experimental variant next to the product library (tuning runs only)."""
+    if out is None and not (force or _stale()):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, f) for f in SOURCES] + ["-o", out or LIB]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfaster_b200.so")
+LIB_PATH = os.environ.get("FQ_LIB") or os.path.join(_HERE, "lib", "libfaster_b200.so")   # FQ_LIB: tuning variants
 _lib = None
 
 EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_set_option", "fq_solve_batch", "fq_solve_multi",

@@ -111,7 +111,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
                                 const int* sfo, const WarpMem& m, int prob, int cand, int lane)
 {
   const int N = a.N, nz = a.nz, nw = a.nw, NY = a.NY, ld = a.ld, ne = a.ne;
-  const double dt = a.dt[cand], dt2 = dt * dt, dt3 = dt2 * dt;
+  const double dt = a.dt[cand], dt2 = dt * dt;
   const double inv1 = 1.0 / dt, inv2 = inv1 * inv1, inv3 = inv2 * inv1;
   const double lim0 = a.lim[prob * 3 + 0], lim1 = a.lim[prob * 3 + 1], lim2 = a.lim[prob * 3 + 2];
   const int P = a.poly_ofs[prob + 1] - a.poly_ofs[prob];

@@ -197,3 +197,75 @@ def test_generic_and_specialised_kernels_agree(built_lib, N, P, ff):
         assert ita.max() > 0 and itb.max() > 0      # iteration counts differ: the two kernels use different pivot rules
     finally:
         s.close()
+
+
+def test_edge_cases_through_the_abi(solver, oracle):
+    """Empty batch, invalid assignment, many-faced polytopes (> 32 faces: more than one pass per segment), duplicated
+    polytopes, tiny and huge time allocations, ragged problems with zero candidates."""
+    pb = cr.make_corridor(77, 3, 10)
+    sig = cr.monotone_sigmas(10, 3)
+    # empty batch
+    f, c, _, _ = solver.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], np.zeros(0), np.zeros((0, 10), np.uint8))
+    assert f.size == 0 and c.size == 0
+    # invalid assignment entry -> argument error, not a crash
+    bad = sig[:4].copy()
+    bad[2, 5] = 3
+    with pytest.raises(capi.FqError):
+        solver.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], np.full(4, 0.5), bad)
+    # N out of range
+    with pytest.raises(capi.FqError):
+        solver.solve_batch(2, pb["x0"], pb["xf"], pb["lim"], [], np.full(1, 0.5), None)
+    # polytopes with many (redundant) faces: 45 faces each
+    rng = np.random.default_rng(3)
+    fat = []
+    for (A, b), (v0, v1) in zip(pb["polys"], zip(pb["verts"][:-1], pb["verts"][1:])):
+        mid = 0.5 * (v0 + v1)
+        n = rng.normal(size=(45 - len(b), 3))
+        n /= np.linalg.norm(n, axis=1, keepdims=True)
+        fat.append((np.vstack([A, n]), np.concatenate([b, n @ mid + rng.uniform(2.5, 4.0, len(n))])))
+    dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], 10)
+    dts = np.repeat(np.array([1.5, 2.0, 3.0, 5.0]) * dti, len(sig))
+    sigs = np.tile(sig, (4, 1))
+    for polys in (fat, [pb["polys"][0], pb["polys"][0], pb["polys"][2]]):
+        fg, cg, cog, _ = solver.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], polys, dts, sigs, True, True)
+        fo, co_, coo = oracle.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], polys, dts, sigs, True, True, threads=8)
+        _compare(fg, cg, cog, fo, co_, coo, "many faces / duplicate polytopes")
+    # extreme time allocations: 2*DC (the floor findDT applies, solverGurobi.cpp:496) and a very slow one
+    for dt in (0.02, 25.0):
+        d = np.full(len(sig), dt)
+        fg, cg, cog, _ = solver.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], d, sig, True, True)
+        fo, co_, coo = oracle.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], d, sig, True, True, threads=8)
+        _compare(fg, cg, cog, fo, co_, coo, "dt=%g" % dt)
+    # ragged multi: a problem with zero candidates in the middle
+    probs = [cr.make_corridor(90 + k, 3, 10) for k in range(3)]
+    rows, face_ofs = [], [0]
+    for p in probs:
+        for A, b in p["polys"]:
+            rows.append(np.hstack([A, b[:, None]])); face_ofs.append(face_ofs[-1] + len(b))
+    cand_ofs = np.array([0, 30, 30, 66], np.int32)
+    dts = np.concatenate([np.full(30, 2.5 * dti), np.full(36, 3.0 * dti)])
+    sg = np.ascontiguousarray(np.vstack([sig[:30], sig[:36]]))
+    fg, cg, cog, _ = solver.solve_multi(10, True, np.ascontiguousarray([p["x0"] for p in probs]),
+                                        np.ascontiguousarray([p["xf"] for p in probs]),
+                                        np.ascontiguousarray([p["lim"] for p in probs]), np.array([0, 3, 6, 9], np.int32),
+                                        np.array(face_ofs, np.int32), np.ascontiguousarray(np.vstack(rows)), cand_ofs, dts, sg,
+                                        want_coeffs=True)
+    for k, (a, b) in enumerate(((0, 30), (30, 30), (30, 66))):
+        if b > a:
+            p = probs[k]
+            fo, co_, coo = oracle.solve_batch(10, p["x0"], p["xf"], p["lim"], p["polys"], dts[a:b], sg[a:b], True, True)
+            _compare(fg[a:b], cg[a:b], cog[a:b], fo, co_, coo, "ragged prob %d" % k)
+
+
+def test_ground_robot_profile(solver, oracle):
+    """BASELINE config 5: ground-robot limits (1.4/1.4/5.0), N=15, 8 narrow polytopes, sampled monotone assignments."""
+    rng = np.random.default_rng(15)
+    N, P = 15, 8
+    pb = cr.make_corridor(555, P, N, "ground", True)
+    sig = cr.sample_monotone_sigmas(N, P, 512, rng)
+    dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N)
+    dts = np.repeat(np.arange(1, 9) * max(dti, 0.02), 64)
+    sigs = np.ascontiguousarray(sig[:512])
+    fg, cg, cog, _ = solver.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, True, True)
+    fo, co_, coo = oracle.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, True, True, threads=8)
+    _compare(fg, cg, cog, fo, co_, coo, "ground robot cfg5")
