@@ -99,10 +99,8 @@ def cpu_reference_rate(n_corr_sample, threads, min_seconds, seed0=900000):
 
     def one_pass():
         for w in (ww, ws):
-            for c, pb in enumerate(w["probs"]):
-                a, b = c * CAND, (c + 1) * CAND
-                po.solve_batch(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], w["dt"][a:b], w["sigma"][a:b],
-                               w["ff"], False, threads)
+            po.solve_multi(N_SEG, w["ff"], w["x0"], w["xf"], w["lim"], w["poly_ofs"], w["face_ofs"], w["Ab"],
+                           w["cand_ofs"], w["dt"], w["sigma"], threads)
     one_pass()                                                      # warm-up
     reps, t0 = 0, time.perf_counter()
     while True:
@@ -130,10 +128,8 @@ def run_reference(args):
 
     def step():
         for w in (ww, ws):
-            for c, pb in enumerate(w["probs"]):
-                a, b = c * CAND, (c + 1) * CAND
-                po.solve_batch(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], w["dt"][a:b], w["sigma"][a:b],
-                               w["ff"], False, threads)
+            po.solve_multi(N_SEG, w["ff"], w["x0"], w["xf"], w["lim"], w["poly_ofs"], w["face_ofs"], w["Ab"],
+                           w["cand_ofs"], w["dt"], w["sigma"], threads)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -330,7 +326,7 @@ def main():
                              "note": "compute/latency-bound FP64 kernel; HBM fraction is tiny by construction (SURVEY 8d)"}}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            rate, sample = cpu_reference_rate(4, threads, args.cpu_seconds)
+            rate, sample = cpu_reference_rate(max(4, threads // 4), threads, args.cpu_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -72,8 +72,11 @@ static void model_build_map(fqo_model* m)
 {
   const int N = m->N, n = 3 * N;
   const double dt = m->dt;
-  memset(m->zc, 0, sizeof(m->zc));
-  memset(m->M, 0, sizeof(m->M));
+  for (int i = 0; i < 12 * N; i++)
+  {
+    m->zc[i] = 0;
+    memset(m->M[i], 0, sizeof(double) * n);
+  }
   for (int ax = 0; ax < 3; ax++)
   {
     /* segment 0: d = p0, c = v0, b = a0/2  (solverGurobi.cpp:369-379) */
@@ -203,8 +206,14 @@ static void row_to_u(const fqo_model* m, const fqo_row* r, double* g, double* c0
  * ------------------------------------------------------------------------------------------- */
 static void gi_init(fqo_state* s, int n)
 {
-  memset(s, 0, sizeof(*s));
-  for (int i = 0; i < n; i++) s->J[i][i] = 1.0;
+  for (int i = 0; i < n; i++)
+  {
+    memset(s->J[i], 0, sizeof(double) * n);
+    memset(s->R[i], 0, sizeof(double) * n);
+    s->J[i][i] = 1.0;
+    s->x[i] = 0; s->lam[i] = 0; s->act[i] = 0;
+  }
+  s->q = 0; s->neq = 0;
 }
 
 static void gi_add(fqo_state* s, int n, double* d, int id, double lam)
@@ -471,14 +480,30 @@ static void write_solution(const fqo_model* m, const fqo_state* s, double* cost,
  * public: one fixed (dt, sigma)
  * returns 1 optimal, 0 infeasible, -1 numeric/iteration cap, -2 bad argument
  * ------------------------------------------------------------------------------------------- */
-int fqo_solve_fixed(int N, int force_final, const double* x0, const double* xf, const double* lim, int P,
-                    const int* face_ofs, const double* Ab, double dt, const uint8_t* sigma, double* cost,
-                    double* coeffs, int* iters)
+/* reusable per-thread workspace (the batch entry points solve many candidates per thread) */
+typedef struct
 {
-  fqo_model* m = (fqo_model*)malloc(sizeof(fqo_model));
-  fqo_state* s = (fqo_state*)malloc(sizeof(fqo_state));
+  fqo_model m;
+  fqo_state s;
+  uint8_t* active;
+  int active_cap;
+} fqo_work;
+
+static fqo_work* work_new(void)
+{
+  fqo_work* w = (fqo_work*)malloc(sizeof(fqo_work));
+  w->active = NULL; w->active_cap = 0;
+  return w;
+}
+static void work_free(fqo_work* w) { if (w) { free(w->active); free(w); } }
+
+static int solve_fixed_ws(fqo_work* w, int N, int force_final, const double* x0, const double* xf, const double* lim,
+                          int P, const int* face_ofs, const double* Ab, double dt, const uint8_t* sigma, double* cost,
+                          double* coeffs, int* iters)
+{
+  fqo_model* m = &w->m;
+  fqo_state* s = &w->s;
   int rc = -2;
-  uint8_t* active = NULL;
   if (iters) *iters = 0;
   if (model_init(m, N, force_final, x0, xf, lim, P, face_ofs, Ab, dt) == 0)
   {
@@ -487,13 +512,24 @@ int fqo_solve_fixed(int N, int force_final, const double* x0, const double* xf, 
     else
     {
       int m_all = n_box(m) + 4 * N * m->SF;
-      active = (uint8_t*)calloc(m_all > 0 ? m_all : 1, 1);
+      if (m_all < 1) m_all = 1;
+      if (m_all > w->active_cap) { free(w->active); w->active = (uint8_t*)malloc(m_all); w->active_cap = m_all; }
+      memset(w->active, 0, m_all);
       fqo_rows rs = { m, sigma, P > 0 ? N : 0 };
-      rc = gi_run(s, &rs, active, iters);
+      rc = gi_run(s, &rs, w->active, iters);
       if (rc == 1) write_solution(m, s, cost, coeffs);
     }
   }
-  free(active); free(s); free(m);
+  return rc;
+}
+
+int fqo_solve_fixed(int N, int force_final, const double* x0, const double* xf, const double* lim, int P,
+                    const int* face_ofs, const double* Ab, double dt, const uint8_t* sigma, double* cost,
+                    double* coeffs, int* iters)
+{
+  fqo_work* w = work_new();
+  int rc = solve_fixed_ws(w, N, force_final, x0, xf, lim, P, face_ofs, Ab, dt, sigma, cost, coeffs, iters);
+  work_free(w);
   return rc;
 }
 
@@ -512,21 +548,34 @@ typedef struct
   int tid, nth;
   /* heterogeneous batches: per-candidate problem index (NULL = single problem) */
   const int* prob;
-  int x_stride;
+  const int* poly_ofs;
 } fqo_job;
 
 static void* batch_worker(void* arg)
 {
   fqo_job* j = (fqo_job*)arg;
+  fqo_work* w = work_new();
   for (int i = j->tid; i < j->n_cand; i += j->nth)
   {
     double c = 0;
-    int rc = fqo_solve_fixed(j->N, j->force_final, j->x0, j->xf, j->lim, j->P, j->face_ofs, j->Ab, j->dt[i],
-                             j->sigma + (size_t)i * j->N, &c, j->coeffs ? j->coeffs + (size_t)i * 12 * j->N : NULL,
-                             NULL);
+    int rc;
+    if (j->prob)
+    { /* heterogeneous batch: candidate i belongs to problem prob[i]; x0/xf/lim/poly_ofs are per problem */
+      const int pr = j->prob[i];
+      const int p0 = j->poly_ofs[pr], P = j->poly_ofs[pr + 1] - p0;
+      int fo[64];
+      const int f0 = j->face_ofs[p0];
+      for (int p = 0; p <= P && p < 64; p++) fo[p] = j->face_ofs[p0 + p] - f0;
+      rc = solve_fixed_ws(w, j->N, j->force_final, j->x0 + 9 * pr, j->xf + 9 * pr, j->lim + 3 * pr, P, fo,
+                          j->Ab + (size_t)4 * f0, j->dt[i], j->sigma + (size_t)i * j->N, &c, NULL, NULL);
+    }
+    else
+      rc = solve_fixed_ws(w, j->N, j->force_final, j->x0, j->xf, j->lim, j->P, j->face_ofs, j->Ab, j->dt[i],
+                          j->sigma + (size_t)i * j->N, &c, j->coeffs ? j->coeffs + (size_t)i * 12 * j->N : NULL, NULL);
     j->feasible[i] = rc == 1;
     j->cost[i] = rc == 1 ? c : INFINITY;
   }
+  work_free(w);
   return NULL;
 }
 
@@ -541,11 +590,36 @@ int fqo_solve_batch(int N, int force_final, const double* x0, const double* xf, 
   for (int t = 0; t < n_threads; t++)
   {
     fqo_job j = { N, force_final, P, x0, xf, lim, face_ofs, Ab, n_cand, dt, sigma, feasible, cost, coeffs, t,
-                  n_threads, NULL, 0 };
+                  n_threads, NULL, NULL };
     jobs[t] = j;
     pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
   }
   for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  return 0;
+}
+
+/* many corridor problems in one call (same layout as the product's fq_solve_multi), threaded over candidates */
+int fqo_solve_multi(int N, int force_final, int n_prob, const double* x0, const double* xf, const double* lim,
+                    const int* poly_ofs, const int* face_ofs, const double* Ab, const int* cand_ofs, const double* dt,
+                    const uint8_t* sigma, uint8_t* feasible, double* cost, int n_threads)
+{
+  const int n_cand = cand_ofs[n_prob];
+  int* prob = (int*)malloc(sizeof(int) * (n_cand > 0 ? n_cand : 1));
+  for (int j = 0; j < n_prob; j++)
+    for (int i = cand_ofs[j]; i < cand_ofs[j + 1]; i++) prob[i] = j;
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  pthread_t th[256];
+  fqo_job jobs[256];
+  for (int t = 0; t < n_threads; t++)
+  {
+    fqo_job j = { N, force_final, 0, x0, xf, lim, face_ofs, Ab, n_cand, dt, sigma, feasible, cost, NULL, t,
+                  n_threads, prob, poly_ofs };
+    jobs[t] = j;
+    pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
+  }
+  for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  free(prob);
   return 0;
 }
 

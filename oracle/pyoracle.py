@@ -89,6 +89,23 @@ def solve_batch(N, x0, xf, lim, polys, dts, sigmas, force_final=True, want_coeff
     return feas, cost, co
 
 
+def solve_multi(N, force_final, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dts, sigmas, threads=1):
+    """Same array layout as the product's fq_solve_multi (host arrays).  -> (feasible, cost)."""
+    L = lib()
+    n_prob = len(cand_ofs) - 1
+    n = int(cand_ofs[-1])
+    c = lambda a, t: np.ascontiguousarray(a, t)
+    x0, xf, lim, Ab, dts = c(x0, np.float64), c(xf, np.float64), c(lim, np.float64), c(Ab, np.float64), c(dts, np.float64)
+    poly_ofs, face_ofs, cand_ofs = c(poly_ofs, np.int32), c(face_ofs, np.int32), c(cand_ofs, np.int32)
+    sig = c(sigmas, np.uint8)
+    feas = np.zeros(n, np.uint8)
+    cost = np.zeros(n)
+    L.fqo_solve_multi(C.c_int(N), C.c_int(int(force_final)), C.c_int(n_prob), x0.ctypes, xf.ctypes, lim.ctypes,
+                      poly_ofs.ctypes, face_ofs.ctypes, Ab.ctypes, cand_ofs.ctypes, dts.ctypes, sig.ctypes,
+                      feas.ctypes, cost.ctypes, C.c_int(threads))
+    return feas, cost
+
+
 def solve_miqp(N, x0, xf, lim, dt, polys, force_final=True):
     """Branch and bound over ALL sigma in P^N -> (status, cost, coeffs, sigma, nodes)."""
     L = lib()

@@ -214,3 +214,25 @@ def test_kernel_mathematics_mirror_vs_oracle(oracle, N, P, ff):
                         assert abs(c - cm) <= 1e-8 * max(1.0, c) and np.abs(co - com).max() <= 1e-7 * max(1.0, np.abs(co).max())
                 n += 1
     assert n >= 8
+
+
+def test_oracle_multi_equals_batches(oracle):
+    """The multi-problem entry used by bench.py's CPU legs gives what the per-problem entry gives."""
+    N, P = 10, 3
+    sig = cr.monotone_sigmas(N, P)
+    probs = [cr.make_corridor(20 + k, P, N) for k in range(3)]
+    poly_ofs, face_ofs, rows, cand_ofs, dts, sigs = [0], [0], [], [0], [], []
+    for k, p in enumerate(probs):
+        for A, b in p["polys"]:
+            rows.append(np.hstack([A, b[:, None]])); face_ofs.append(face_ofs[-1] + len(b))
+        poly_ofs.append(poly_ofs[-1] + P)
+        dti = capi.dt_initial(p["x0"], p["xf"], p["lim"], N)
+        n = 15 + 4 * k
+        dts.append((1.5 + 0.5 * np.arange(n)) * dti); sigs.append(sig[(3 * np.arange(n)) % len(sig)])
+        cand_ofs.append(cand_ofs[-1] + n)
+    f, c = oracle.solve_multi(N, True, [p["x0"] for p in probs], [p["xf"] for p in probs], [p["lim"] for p in probs],
+                              poly_ofs, face_ofs, np.vstack(rows), cand_ofs, np.concatenate(dts), np.vstack(sigs), threads=3)
+    for k, p in enumerate(probs):
+        fo, co_, _ = oracle.solve_batch(N, p["x0"], p["xf"], p["lim"], p["polys"], dts[k], sigs[k], True)
+        a, b = cand_ofs[k], cand_ofs[k + 1]
+        assert np.array_equal(f[a:b], fo) and np.array_equal(c[a:b], co_)
