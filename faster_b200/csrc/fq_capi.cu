@@ -253,8 +253,13 @@ int describe(fq_ctx* ctx, int N, int force_final, int n_prob, const int* poly_of
       if (face_ofs[p + 1] - face_ofs[p] > *max_poly_faces) *max_poly_faces = face_ofs[p + 1] - face_ofs[p];
     }
     if (P > 0 && sigma)
-      for (size_t i = (size_t)cand_ofs[j] * N; i < (size_t)cand_ofs[j + 1] * N; i++)
-        if (sigma[i] >= P) return fail(ctx, FQ_E_ARG, "sigma entry >= number of polytopes");
+    { // branch-free max over the bytes (vectorises); one compare per problem
+      const uint8_t* sp = sigma + (size_t)cand_ofs[j] * N;
+      const size_t cnt = (size_t)nc * N;
+      unsigned mx = 0;
+      for (size_t i = 0; i < cnt; i++) mx = sp[i] > mx ? sp[i] : mx;
+      if ((int)mx >= P) return fail(ctx, FQ_E_ARG, "sigma entry >= number of polytopes");
+    }
     if (nc > *max_cand) *max_cand = nc;
     if (nf > *max_faces) *max_faces = nf;
   }
@@ -264,11 +269,11 @@ int describe(fq_ctx* ctx, int N, int force_final, int n_prob, const int* poly_of
   L->x0 = o;        o += sizeof(double) * 9 * (size_t)n_prob;
   L->xf = o;        o += sizeof(double) * 9 * (size_t)n_prob;
   L->lim = o;       o += sizeof(double) * 3 * (size_t)n_prob;
-  L->dt = o;        o += sizeof(double) * (size_t)*n_cand;
   L->poly_ofs = o;  o += sizeof(int) * (size_t)(n_prob + 1);
   L->face_ofs = o;  o += sizeof(int) * (size_t)(*n_poly + 1);
-  L->cand_ofs = o;  o += sizeof(int) * (size_t)(n_prob + 1);
-  L->sigma = o;     o += (size_t)*n_cand * N;
+  L->cand_ofs = o;  o = align16(o + sizeof(int) * (size_t)(n_prob + 1));
+  L->dt = o;        o += sizeof(double) * (size_t)*n_cand;      // per-candidate arrays last: [0, dt) is the
+  L->sigma = o;     o += (size_t)*n_cand * N;                   // per-problem description
   L->in_bytes = align16(o);
   o = 0;
   L->cost = o;      o += sizeof(double) * (size_t)*n_cand;
@@ -320,9 +325,17 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
     FQ_CUDA(cudaMemcpyAsync(din, ctx->h_in.p, L.in_bytes, cudaMemcpyHostToDevice, st));
   }
   else
-  { // throughput path: DMA straight from the caller's buffers (true async when they are pinned)
+  { // throughput path: the per-candidate arrays (dt, sigma) are DMA'd straight from the caller's buffers (true
+    // async when they are pinned); the per-problem description is small and goes through one staged copy
+    const bool pack_head = L.dt <= kPackThreshold;
+    if (pack_head) FQ_CUDA(ctx->h_in.reserve(L.dt));
     for (const Piece& p : pieces)
-      if (p.bytes) FQ_CUDA(cudaMemcpyAsync(din + p.off, p.src, p.bytes, cudaMemcpyHostToDevice, st));
+    {
+      if (!p.bytes) continue;
+      if (pack_head && p.off < L.dt) std::memcpy((char*)ctx->h_in.p + p.off, p.src, p.bytes);
+      else FQ_CUDA(cudaMemcpyAsync(din + p.off, p.src, p.bytes, cudaMemcpyHostToDevice, st));
+    }
+    if (pack_head) FQ_CUDA(cudaMemcpyAsync(din, ctx->h_in.p, L.dt, cudaMemcpyHostToDevice, st));
   }
   if (n_poly == 0) FQ_CUDA(cudaMemsetAsync(din + L.sigma, 0, sig_bytes, st));
   rc = launch_solve(ctx, N, force_final, n_prob, (const double*)(din + L.x0), (const double*)(din + L.xf),

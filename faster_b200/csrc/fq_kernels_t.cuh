@@ -89,7 +89,7 @@ __device__ __forceinline__ int rank_key(double u) { return __double2hiint(u); }
 
 // Y = Yeq + TZ w for the lane's rows, box rows checked on the fly.  Updates the lane's best (key, code).
 // bthr[r] = (limit + tol) * dt^k for box rows (huge for other rows), srow[r] = S[y].
-template <class D>
+template <class D, bool ZERO_W = false>
 __device__ __forceinline__ void update_Y(const WarpState<D>& m, const double* __restrict__ TZ,
                                          const double (&Yeq)[D::RPL][3], const double (&bthr)[D::RPL],
                                          const double (&srow)[D::RPL], int lane, int& bkey, unsigned& bcode)
@@ -100,7 +100,7 @@ __device__ __forceinline__ void update_Y(const WarpState<D>& m, const double* __
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) acc[r][ax] = Yeq[r][ax];
 #pragma unroll
-  for (int k = 0; k < D::NZ; k++)
+  for (int k = 0; k < (ZERO_W ? 0 : D::NZ); k++)      // ZERO_W: first evaluation of a candidate, w = 0
   {
     const double w0 = m.w[k], w1 = m.w[D::NZ + k], w2 = m.w[2 * D::NZ + k];
 #pragma unroll
@@ -303,7 +303,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
   int q = 0, status = -2, it = 0;
   int bkey = 0;
   unsigned bcode = 0;
-  update_Y<D>(m, TZ, Yeq, bthr, srow, lane, bkey, bcode);
+  update_Y<D, true>(m, TZ, Yeq, bthr, srow, lane, bkey, bcode);
   while (status == -2)
   {
     // ================= most violated corridor row (box rows were checked by update_Y) =================
@@ -400,7 +400,6 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
           }
         }
       }
-      const double zz = warp_sum(zzp);
       __syncwarp();
       // ---- z = -J2 d2 (lane-owned rows)
 #pragma unroll
@@ -439,8 +438,8 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
           else if (j == k) r[s] = rk;
         }
       }
-      const bool dep = zz <= fmax(FQ_EPS_DEP * gg, FQ_ZZ_FLOOR);
-      // ---- dual ratio test
+      // ---- dual ratio test, |d2|^2 and the step scalars in one straight-line block: the two shuffle trees and the
+      //      MUFU seeds are independent, so their latencies overlap
       double best = INFINITY;
       int bk = -1;
 #pragma unroll
@@ -453,18 +452,27 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
           if (ratio < best) { best = ratio; bk = k; }
         }
       }
-      const double t1 = warp_min(best);
+      double zz = zzp, t1 = best;
+#pragma unroll
+      for (int o = 16; o; o >>= 1)
+      {
+        zz += __shfl_xor_sync(FULL, zz, o);
+        t1 = fmin(t1, __shfl_xor_sync(FULL, t1, o));
+      }
+      const double zzs = fmax(zz, 1e-300);
+      const double rn = fast_rsqrt(zzs), rzz = fast_rcp(zzs);
+      const bool dep = zz <= fmax(FQ_EPS_DEP * gg, FQ_ZZ_FLOOR);
       int l = -1;
       if (t1 < INFINITY)
       {
         const int s2 = __ffs(__ballot_sync(FULL, best == t1)) - 1;
         l = __shfl_sync(FULL, bk, s2);
       }
-      const double t2 = dep ? INFINITY : viol * fast_rcp(zz);
+      const double t2 = dep ? INFINITY : viol * rzz;
       if (t1 == INFINITY && t2 == INFINITY) { status = 0; break; }
       if (t2 <= t1)
       { // ---- full step: the row becomes active
-        const double rn = fast_rsqrt(zz), nrm = zz * rn;
+        const double nrm = zz * rn;
         const double dq = m.d[q], sgn = dq >= 0 ? 1.0 : -1.0;
         const double beta = fast_rcp(fma(fabs(dq), nrm, zz)), vq = fma(sgn, nrm, dq);
 #pragma unroll

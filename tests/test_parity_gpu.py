@@ -269,3 +269,43 @@ def test_ground_robot_profile(solver, oracle):
     fg, cg, cog, _ = solver.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, True, True)
     fo, co_, coo = oracle.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, True, True, threads=8)
     _compare(fg, cg, cog, fo, co_, coo, "ground robot cfg5")
+
+
+def test_device_pointer_entry_matches_host_entry(solver):
+    """fq_solve_multi_dev (device-resident inputs, caller's stream, no sync inside) == fq_solve_multi."""
+    import torch
+    N, P = 10, 4
+    sig = cr.monotone_sigmas(N, P)
+    probs = [cr.make_corridor(130 + k, P, N, force_final=False) for k in range(6)]
+    poly_ofs, face_ofs, rows, cand_ofs, dts, sigs = [0], [0], [], [0], [], []
+    for k, p in enumerate(probs):
+        for A, b in p["polys"]:
+            rows.append(np.hstack([A, b[:, None]])); face_ofs.append(face_ofs[-1] + len(b))
+        poly_ofs.append(poly_ofs[-1] + P)
+        dti = capi.dt_initial(p["x0"], p["xf"], p["lim"], N)
+        n = 100 + 13 * k
+        dts.append((1.0 + 0.1 * np.arange(n)) * dti); sigs.append(sig[(7 * np.arange(n)) % len(sig)])
+        cand_ofs.append(cand_ofs[-1] + n)
+    h = dict(x0=np.ascontiguousarray([p["x0"] for p in probs]), xf=np.ascontiguousarray([p["xf"] for p in probs]),
+             lim=np.ascontiguousarray([p["lim"] for p in probs]), poly_ofs=np.array(poly_ofs, np.int32),
+             face_ofs=np.array(face_ofs, np.int32), Ab=np.ascontiguousarray(np.vstack(rows)),
+             cand_ofs=np.array(cand_ofs, np.int32), dt=np.concatenate(dts), sigma=np.ascontiguousarray(np.vstack(sigs)))
+    fh, ch, coh, _ = solver.solve_multi(N, False, h["x0"], h["xf"], h["lim"], h["poly_ofs"], h["face_ofs"], h["Ab"],
+                                        h["cand_ofs"], h["dt"], h["sigma"], want_coeffs=True)
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(v).to(dev) for k, v in h.items()}
+    n = int(cand_ofs[-1])
+    feas = torch.zeros(n, dtype=torch.uint8, device=dev)
+    cost = torch.zeros(n, dtype=torch.float64, device=dev)
+    coef = torch.zeros(n * N * 12, dtype=torch.float64, device=dev)
+    st = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        solver.solve_multi_dev(N, False, len(probs), d["x0"].data_ptr(), d["xf"].data_ptr(), d["lim"].data_ptr(),
+                               d["poly_ofs"].data_ptr(), d["face_ofs"].data_ptr(), d["Ab"].data_ptr(),
+                               d["cand_ofs"].data_ptr(), int(np.diff(cand_ofs).max()),
+                               int(max(face_ofs[poly_ofs[j + 1]] - face_ofs[poly_ofs[j]] for j in range(len(probs)))),
+                               d["dt"].data_ptr(), d["sigma"].data_ptr(), feas.data_ptr(), cost.data_ptr(),
+                               coef.data_ptr(), 0, st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(feas.cpu().numpy(), fh) and np.array_equal(cost.cpu().numpy(), ch)
+    assert np.array_equal(coef.cpu().numpy().reshape(n, N, 12), coh)
