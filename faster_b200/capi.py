@@ -12,7 +12,7 @@ _lib = None
 
 EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_set_option", "fq_solve_batch", "fq_solve_multi",
            "fq_solve_multi_dev", "fq_gen_new_traj", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
-           "fq_monotone_sigmas", "fq_plan_tables"]
+           "fq_monotone_sigmas", "fq_plan_tables", "fq_ellipsoid_decomp"]
 
 
 class FqError(RuntimeError):
@@ -37,6 +37,8 @@ def lib():
         L.fq_monotone_sigmas.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_long]
         L.fq_plan_tables.restype = C.c_int
         L.fq_plan_tables.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fq_ellipsoid_decomp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double,
+                                          C.c_void_p, C.c_void_p, C.c_int]
         L.fq_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.fq_destroy.argtypes = [C.c_void_p]
         L.fq_destroy.restype = None
@@ -93,6 +95,22 @@ def monotone_sigmas(N, P):
     out = np.zeros((n, N), np.uint8)
     lib().fq_monotone_sigmas(int(N), int(P), out.ctypes.data, n)
     return out
+
+
+def ellipsoid_decomp(path, obs, bbox=(2.0, 2.0, 1.0), inflate=0.42, z_ground=0.0, cap_rows=4096):
+    """Host-side convex decomposition (fq_ellipsoid_decomp) -> list of (A[F,3], b[F]), one polytope per path segment."""
+    path = np.ascontiguousarray(np.asarray(path, np.float64).reshape(-1, 3))
+    obs = np.ascontiguousarray(np.asarray(obs, np.float64).reshape(-1, 3))
+    n_seg = path.shape[0] - 1
+    bb = _f64(bbox, 3)
+    ofs = np.zeros(n_seg + 1, np.int32)
+    Ab = np.zeros((cap_rows, 4))
+    rows = lib().fq_ellipsoid_decomp(path.ctypes.data, n_seg, obs.ctypes.data if len(obs) else None, len(obs),
+                                     bb.ctypes.data, float(inflate), float(z_ground), ofs.ctypes.data, Ab.ctypes.data,
+                                     cap_rows)
+    if rows < 0:
+        raise FqError("fq_ellipsoid_decomp failed (%d)" % rows)
+    return [(Ab[ofs[i]:ofs[i + 1], :3].copy(), Ab[ofs[i]:ofs[i + 1], 3].copy()) for i in range(n_seg)]
 
 
 def plan_tables(N, force_final):

@@ -98,3 +98,73 @@ def make_corridor(seed, P, N, profile="uav", force_final=True, DC=0.01):
     xf[:3] = verts[-1]
     return dict(N=N, P=P, x0=x0, xf=xf, lim=np.array(prof["lim"]), polys=polys, force_final=bool(force_final),
                 DC=DC, verts=np.array(verts), seed=seed, profile=profile)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Random-forest corridors (BASELINE config 4): obstacle point cloud -> polyline -> convex decomposition -> polytopes.
+# The polyline stands in for the JPS3D path (out of scope); the decomposition is the product's
+# host-side restatement of JPS_Manager::cvxEllipsoidDecomp (faster_b200/csrc/fq_decomp.cpp).
+# ------------------------------------------------------------------------------------------------------------------
+def make_forest(seed, n_trees=60, area=16.0, height=3.0, res=0.15):
+    """Vertical cylinders (radius U[0.1,0.3], density ~ launch/ground_robot.launch 'density01') sampled on their
+    surface at `res` metres, like a voxelised map.  -> (points [n,3], centres [n_trees,2], radii [n_trees])."""
+    rng = np.random.default_rng(seed)
+    centres = rng.uniform(-area / 2, area / 2, (n_trees, 2))
+    radii = rng.uniform(0.1, 0.3, n_trees)
+    pts = []
+    for c, r in zip(centres, radii):
+        th = np.arange(0, 2 * np.pi, res / r)
+        zs = np.arange(0.0, height, res)
+        ring = np.stack([c[0] + r * np.cos(th), c[1] + r * np.sin(th)], axis=1)
+        pts.append(np.concatenate([np.hstack([ring, np.full((len(ring), 1), z)]) for z in zs]))
+    return np.concatenate(pts), centres, radii
+
+
+def _seg_point_dist_xy(a, b, c):
+    ab = b - a
+    t = np.clip(((c - a) @ ab) / max(ab @ ab, 1e-12), 0.0, 1.0)
+    return np.linalg.norm(a + t * ab - c)
+
+
+def forest_path(seed, centres, radii, n_seg, clearance, seg_len=(1.0, 1.5), z=(0.8, 1.4), area=16.0, tries=4000):
+    """Polyline of n_seg segments whose every segment keeps `clearance` from every tree (xy distance to the axis minus
+    the radius).  Rejection sampling; raises if the forest is too dense."""
+    rng = np.random.default_rng(seed)
+    for _ in range(tries):
+        p = np.array([rng.uniform(-area / 2 + 2, area / 2 - 2), rng.uniform(-area / 2 + 2, area / 2 - 2), rng.uniform(*z)])
+        yaw = rng.uniform(-np.pi, np.pi)
+        verts, ok = [p], True
+        for _s in range(n_seg):
+            yaw += np.deg2rad(rng.uniform(-50, 50))
+            L = rng.uniform(*seg_len)
+            q = verts[-1] + np.array([L * np.cos(yaw), L * np.sin(yaw), 0.0])
+            q[2] = rng.uniform(*z)
+            if any(_seg_point_dist_xy(verts[-1][:2], q[:2], c) - r < clearance for c, r in zip(centres, radii)):
+                ok = False
+                break
+            verts.append(q)
+        if ok:
+            return np.array(verts)
+    raise RuntimeError("no collision-free polyline found")
+
+
+def make_forest_corridor(seed, P, N, force_final=True, decomp=None, DC=0.01, n_trees=60):
+    """Corridor problem whose polytopes come from the convex decomposition of a random forest around a polyline.
+    decomp(path, obs, bbox, inflate, z_ground) -> [(A,b)...]; default = the product's fq_ellipsoid_decomp."""
+    if decomp is None:
+        from . import capi
+        decomp = capi.ellipsoid_decomp
+    prof = UAV
+    obs, centres, radii = make_forest(seed, n_trees=n_trees)
+    verts = forest_path(seed + 1, centres, radii, P, clearance=prof["drone_radius"] * 1.45 + 0.05)
+    polys = decomp(verts, obs, prof["bbox"], prof["drone_radius"], prof["z_ground"])
+    rng = np.random.default_rng(seed + 2)
+    d0 = verts[1] - verts[0]
+    d0 /= np.linalg.norm(d0)
+    x0 = np.zeros(9)
+    x0[:3] = verts[0]
+    x0[3:6] = d0 * rng.uniform(*prof["v0"])
+    xf = np.zeros(9)
+    xf[:3] = verts[-1]
+    return dict(N=N, P=P, x0=x0, xf=xf, lim=np.array(prof["lim"]), polys=polys, force_final=bool(force_final), DC=DC,
+                verts=verts, obs=obs, seed=seed, profile="uav")

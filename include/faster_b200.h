@@ -110,6 +110,16 @@ void fq_fill_x(int N, const double* coeffs, double dt, double DC, int n_samples,
  * lexicographic order. */
 long fq_monotone_sigmas(int N, int P, uint8_t* out, long cap);
 
+/* Convex decomposition of a polyline path against an obstacle point cloud -- the host-side input generator that feeds
+ * setPolytopes in the reference: JPS_Manager::cvxEllipsoidDecomp (faster/src/jps_manager.cpp:80-127) over DecompUtil's
+ * EllipsoidDecomp3D (line_segment.h:156-252 ellipsoid, decomp_base.h:83-115 polyhedron, line_segment.h:57-98 local
+ * bbox), sign normalisation w.r.t. the segment midpoint (polyhedron.h:131-152) and the ground face appended last.
+ *   path (n_seg+1) x 3, obs n_obs x 3, bbox[3] = local bounding box (reference: 2,2,1), inflate = drone radius.
+ * Writes face_ofs[n_seg+1] and rows [Ax Ay Az b] into Ab (capacity cap_rows rows).  Returns the number of rows, or
+ * FQ_E_NOMEM if cap_rows is too small, FQ_E_ARG on bad input.  Pure host code. */
+int fq_ellipsoid_decomp(const double* path, int n_seg, const double* obs, int n_obs, const double* bbox,
+                        double inflate, double z_ground, int* face_ofs, double* Ab, int cap_rows);
+
 /* Introspection (tests): copies the per-(N, force_final) plan tables documented in faster_b200/csrc/fq_plan.h.
  * Returns NY = 6N+1, or 0 if (N, force_final) is unsupported.  TZ: NY*(N-ne), T0: NY*(3+ne), FT: ne*3,
  * ne = force_final ? 3 : 2.  Any pointer may be NULL. */

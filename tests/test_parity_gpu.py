@@ -309,3 +309,53 @@ def test_device_pointer_entry_matches_host_entry(solver):
     st.synchronize()
     assert np.array_equal(feas.cpu().numpy(), fh) and np.array_equal(cost.cpu().numpy(), ch)
     assert np.array_equal(coef.cpu().numpy().reshape(n, N, 12), coh)
+
+
+def test_forest_paired_whole_then_safe(solver, oracle):
+    """BASELINE config 4 in miniature: random-forest point cloud -> polyline -> convex decomposition (product host code)
+    -> whole sweep -> the safe problem starts from a sample of the whole trajectory (faster.cpp:475) with its own
+    decomposition -> safe sweep.  Every stage is compared with the oracle run on the same inputs."""
+    from oracle import decomp_oracle as do
+    DC, N = 0.01, 10
+    done = 0
+    for seed in range(200, 212):
+        try:
+            pb = cr.make_forest_corridor(seed, 3, N, True)
+        except RuntimeError:
+            continue
+        polys_o = do.cvx_ellipsoid_decomp(pb["verts"], pb["obs"], (2.0, 2.0, 1.0), 0.42, 0.0)
+        assert all(a.shape == b.shape for (a, _), (b, _) in zip(pb["polys"], polys_o))
+        sig = cr.monotone_sigmas(N, 3)
+        dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N)
+        facs = np.arange(1.0, 11.0)
+        g = solver.gen_new_traj(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], facs * max(dti, 2 * DC), sig, True)
+        o = oracle.gen_new_traj(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], DC, 1.0, 10.0, 1.0, None, True)
+        assert g["solved"] == o["solved"]
+        if not o["solved"]:
+            continue
+        assert facs[g["dt_index"]] == o["factor"] and abs(g["cost"] - o["cost"]) <= REL * max(1.0, o["cost"])
+        dt = o["dt"]
+        X = capi.fill_x(N, g["coeffs"], dt, DC)
+        R = X[int(0.6 * len(X))]                                  # stand-in for findIndexR's choice
+        j = int(np.argmin([np.linalg.norm(np.cross(R[:3] - pb["verts"][k], pb["verts"][k + 1] - pb["verts"][k]))
+                           / np.linalg.norm(pb["verts"][k + 1] - pb["verts"][k]) for k in range(3)]))
+        safe_path = np.vstack([R[:3], pb["verts"][j + 1:]])
+        if len(safe_path) < 2 or np.linalg.norm(safe_path[1] - safe_path[0]) < 0.05:
+            continue
+        spolys = capi.ellipsoid_decomp(safe_path, pb["obs"], (2.0, 2.0, 1.0), 0.42, 0.0)
+        Ps = len(spolys)
+        x0s = np.concatenate([R[:3], R[3:6], R[6:9]])
+        xfs = np.zeros(9)
+        xfs[:3] = safe_path[-1]
+        sigs = cr.monotone_sigmas(N, Ps)
+        dtis = capi.dt_initial(x0s, xfs, pb["lim"], N)
+        gs = solver.gen_new_traj(N, x0s, xfs, pb["lim"], spolys, facs * max(dtis, 2 * DC), sigs, False)
+        os_ = oracle.gen_new_traj(N, x0s, xfs, pb["lim"], spolys, DC, 1.0, 10.0, 1.0, None, False)
+        assert gs["solved"] == os_["solved"]
+        if os_["solved"]:
+            assert facs[gs["dt_index"]] == os_["factor"]
+            assert abs(gs["cost"] - os_["cost"]) <= REL * max(1.0, os_["cost"])
+            assert np.abs(gs["coeffs"] - os_["coeffs"]).max() <= 1e-6 * max(1.0, np.abs(os_["coeffs"]).max())
+            assert np.allclose(gs["coeffs"][0, 9:12], R[:3], atol=1e-9)      # safe trajectory starts at R
+            done += 1
+    assert done >= 3
