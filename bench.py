@@ -338,7 +338,26 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                              "algorithmic_bytes_per_candidate": BYTES_PER_CAND,
                              "note": "compute/latency-bound FP64 kernel; HBM fraction is tiny by construction (SURVEY 8d)"}}
+        line["config"]["iteration_cap_hits"] = int((torch.cat([outs_d[0][2], outs_d[1][2]]) < 0).sum())
         if not args.no_cpu_baseline:
+            # checker: the first corridors of this very workload re-solved by the CPU restatement
+            from oracle import pyoracle as po
+            nchk = min(C, 8)
+            mism, worst = 0, 0.0
+            for w, o in zip(works, outs_d):
+                sub = dict(w)
+                fo, co = po.solve_multi(N_SEG, w["ff"], w["x0"][:nchk], w["xf"][:nchk], w["lim"][:nchk],
+                                        w["poly_ofs"][:nchk + 1], w["face_ofs"][:w["poly_ofs"][nchk] + 1],
+                                        w["Ab"][:w["face_ofs"][w["poly_ofs"][nchk]]], w["cand_ofs"][:nchk + 1],
+                                        w["dt"][:nchk * CAND], w["sigma"][:nchk * CAND], os.cpu_count() or 1)
+                fg = o[0][:nchk * CAND].cpu().numpy()
+                cg = o[1][:nchk * CAND].cpu().numpy()
+                mism += int((fg != fo).sum())
+                ok = fo.astype(bool) & fg.astype(bool)
+                if ok.any():
+                    worst = max(worst, float((np.abs(cg[ok] - co[ok]) / np.maximum(1e-9, np.abs(co[ok]))).max()))
+            line["parity"] = {"checked_candidates": 2 * nchk * CAND, "flag_mismatches": mism, "max_rel_cost_err": worst,
+                              "against": "oracle/fq_oracle.c (CPU restatement), same inputs"}
             threads = os.cpu_count() or 1
             rate, sample = cpu_reference_rate(max(4, threads // 4), threads, args.cpu_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample}
