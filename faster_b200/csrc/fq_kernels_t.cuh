@@ -92,7 +92,7 @@ __device__ __forceinline__ int rank_key(double u) { return __double2hiint(u); }
 template <class D, bool ZERO_W = false>
 __device__ __forceinline__ void update_Y(const WarpState<D>& m, const double* __restrict__ TZ,
                                          const double (&Yeq)[D::RPL][3], const double (&bthr)[D::RPL],
-                                         const double (&srow)[D::RPL], int lane, int& bkey, unsigned& bcode)
+                                         const double* __restrict__ SY, int lane, int& bkey, unsigned& bcode)
 {
   double acc[D::RPL][3];
 #pragma unroll
@@ -122,11 +122,12 @@ __device__ __forceinline__ void update_Y(const WarpState<D>& m, const double* __
     const int y = lane + 32 * r;
     if (y < D::NY)
     {
+      const double sr = SY[y];
 #pragma unroll
       for (int ax = 0; ax < 3; ax++)
       {
         m.Y[ax * D::NYP + y] = acc[r][ax];
-        const int key = rank_key((fabs(acc[r][ax]) - bthr[r]) * srow[r]);
+        const int key = rank_key((fabs(acc[r][ax]) - bthr[r]) * sr);
         if (key > bkey) { bkey = key; bcode = BOX_FLAG | (unsigned)(ax << 8) | (unsigned)y; }
       }
     }
@@ -199,8 +200,7 @@ template <class D>
 __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict__ TZ,
                                 const double* __restrict__ SY, const double* __restrict__ sAb,
                                 const int* __restrict__ sfo, const WarpState<D>& m, int* __restrict__ seg_ofs,
-                                int prob, int cand, int lane, const double (&btype)[D::RPL],
-                                const double (&srow)[D::RPL])
+                                int prob, int cand, int lane)
 {
   constexpr int N = D::N, NZ = D::NZ, NW = D::NW, NY = D::NY, NYP = D::NYP, LD = D::LD, NE = D::NE, SLOTS = D::SLOTS;
   const double dt = a.dt[cand], dt2 = dt * dt;
@@ -232,9 +232,10 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
     for (int r = 0; r < D::RPL; r++)
     {
       const int y = lane + 32 * r;
-      const double ty = btype[r];                // 0 none, 1 v, 2 a, 3 j
-      bthr[r] = ty == 1.0 ? (lim0 + FQ_ROW_TOL) * dt : (ty == 2.0 ? (lim1 + FQ_ROW_TOL) * dt2
-                                                                    : (ty == 3.0 ? (lim2 + FQ_ROW_TOL) * dt2 * dt : 1e300));
+      // box type of the row: v (rows N+1..2N), a (2N+1..3N), j (3N+1..4N), none otherwise
+      bthr[r] = (y >= N + 1 && y <= 2 * N) ? (lim0 + FQ_ROW_TOL) * dt
+                : ((y >= 2 * N + 1 && y <= 3 * N) ? (lim1 + FQ_ROW_TOL) * dt2
+                                                  : ((y >= 3 * N + 1 && y <= 4 * N) ? (lim2 + FQ_ROW_TOL) * dt2 * dt : 1e300));
 #pragma unroll
       for (int ax = 0; ax < 3; ax++) Yeq[r][ax] = 0.0;
       if (y < NY)
@@ -303,7 +304,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
   int q = 0, status = -2, it = 0;
   int bkey = 0;
   unsigned bcode = 0;
-  update_Y<D, true>(m, TZ, Yeq, bthr, srow, lane, bkey, bcode);
+  update_Y<D, true>(m, TZ, Yeq, bthr, SY, lane, bkey, bcode);
   while (status == -2)
   {
     // ================= most violated corridor row (box rows were checked by update_Y) =================
@@ -494,7 +495,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
         q++;
         __syncwarp();
         bkey = 0; bcode = 0;
-        update_Y<D>(m, TZ, Yeq, bthr, srow, lane, bkey, bcode);
+        update_Y<D>(m, TZ, Yeq, bthr, SY, lane, bkey, bcode);
         break;
       }
       // ---- partial step: active element l leaves
@@ -513,7 +514,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
       {
         int dummy_k = 0;
         unsigned dummy_c = 0;
-        update_Y<D>(m, TZ, Yeq, bthr, srow, lane, dummy_k, dummy_c);
+        update_Y<D>(m, TZ, Yeq, bthr, SY, lane, dummy_k, dummy_c);
       }
     }
   }
@@ -598,15 +599,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <
     m.items = reinterpret_cast<unsigned short*>(p);
     seg_ofs = sfo + 40 + warp * 32;
   }
-  double btype[D::RPL], srow[D::RPL];
   __syncthreads();
-#pragma unroll
-  for (int r = 0; r < D::RPL; r++)
-  { // box type of the lane's rows: 1 v (rows N+1..2N), 2 a (2N+1..3N), 3 j (3N+1..4N), 0 otherwise
-    const int y = lane + 32 * r;
-    btype[r] = (y >= N_ + 1 && y <= 2 * N_) ? 1.0 : ((y >= 2 * N_ + 1 && y <= 3 * N_) ? 2.0 : ((y >= 3 * N_ + 1 && y <= 4 * N_) ? 3.0 : 0.0));
-    srow[r] = y < D::NY ? SY[y] : 0.0;
-  }
   const int n_prob = a.n_prob;
   int cursor = (int)(((long long)blockIdx.x * n_prob) / gridDim.x);   // CTA-specific starting problem
   int visited = 0;
@@ -655,7 +648,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <
       if (lane == 0) c = atomicAdd(counters + prob, 1);
       c = __shfl_sync(FULL, c, 0);
       if (c >= count) break;
-      solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, c_begin + c, lane, btype, srow);
+      solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, c_begin + c, lane);
     }
     __syncthreads();                               // everyone is done with the staged rows
   }

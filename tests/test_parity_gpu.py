@@ -359,3 +359,29 @@ def test_forest_paired_whole_then_safe(solver, oracle):
             assert np.allclose(gs["coeffs"][0, 9:12], R[:3], atol=1e-9)      # safe trajectory starts at R
             done += 1
     assert done >= 3
+
+
+def test_throughput_copy_path_matches_latency_path(solver):
+    """fq_solve_multi stages small inputs through one pinned buffer and DMAs large ones straight from the caller's
+    arrays (> 512 KB): both paths must give identical bits."""
+    N, P = 10, 3
+    sig = cr.monotone_sigmas(N, P)
+    probs = [cr.make_corridor(900 + k, P, N) for k in range(40)]
+    poly_ofs, face_ofs, rows, cand_ofs, dts, sigs = [0], [0], [], [0], [], []
+    for k, p in enumerate(probs):
+        for A, b in p["polys"]:
+            rows.append(np.hstack([A, b[:, None]])); face_ofs.append(face_ofs[-1] + len(b))
+        poly_ofs.append(poly_ofs[-1] + P)
+        dti = capi.dt_initial(p["x0"], p["xf"], p["lim"], N)
+        dts.append(np.repeat(np.arange(1, 17) * dti, len(sig))); sigs.append(np.tile(sig, (16, 1)))
+        cand_ofs.append(cand_ofs[-1] + 16 * len(sig))
+    x0 = np.ascontiguousarray([p["x0"] for p in probs]); xf = np.ascontiguousarray([p["xf"] for p in probs])
+    lim = np.ascontiguousarray([p["lim"] for p in probs]); Ab = np.ascontiguousarray(np.vstack(rows))
+    po, fo, co = np.array(poly_ofs, np.int32), np.array(face_ofs, np.int32), np.array(cand_ofs, np.int32)
+    dt_all, sig_all = np.concatenate(dts), np.ascontiguousarray(np.vstack(sigs))
+    assert dt_all.size * (8 + N) > 512 * 1024                      # forces the throughput path
+    f_big, c_big, _, _ = solver.solve_multi(N, True, x0, xf, lim, po, fo, Ab, co, dt_all, sig_all)
+    for k in (0, 17, 39):                                          # the same problems one by one: latency path
+        a, b = cand_ofs[k], cand_ofs[k + 1]
+        f1, c1, _, _ = solver.solve_batch(N, probs[k]["x0"], probs[k]["xf"], probs[k]["lim"], probs[k]["polys"], dts[k], sigs[k])
+        assert np.array_equal(f_big[a:b], f1) and np.array_equal(c_big[a:b], c1)
