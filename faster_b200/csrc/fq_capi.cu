@@ -119,6 +119,22 @@ void fill_plan_args(const PlanDev& pd, FqKernelArgs* a)
 }
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// branch-free scans (vectorise): x - x == 0 iff x is finite
+inline bool all_finite(const double* p, size_t n)
+{
+  if (!p) return n == 0;
+  double acc = 0;
+  for (size_t i = 0; i < n; i++) acc += (p[i] - p[i]) * (p[i] - p[i]);
+  return acc == 0;
+}
+inline bool all_positive_finite(const double* p, size_t n)
+{
+  if (!all_finite(p, n)) return false;
+  double mn = 1.0;
+  for (size_t i = 0; i < n; i++) mn = p[i] < mn ? p[i] : mn;
+  return mn > 0;
+}
 }  // namespace
 
 extern "C" int fq_create(fq_ctx** out, int device)
@@ -302,6 +318,11 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
   if (rc) return rc;
   if (n_cand == 0) return 0;
   if (n_poly > 0 && (!Ab || !sigma)) return fail(ctx, FQ_E_ARG, "polytopes given but Ab or sigma is NULL");
+  if (!all_finite(x0, 9 * (size_t)n_prob) || !all_finite(xf, 9 * (size_t)n_prob) || !all_finite(lim, 3 * (size_t)n_prob) ||
+      !all_finite(Ab, 4 * (size_t)n_face))
+    return fail(ctx, FQ_E_ARG, "non-finite value in x0/xf/lim/Ab");
+  if (!all_positive_finite(dt, (size_t)n_cand)) return fail(ctx, FQ_E_ARG, "dt must be finite and > 0");
+  if (!all_positive_finite(lim, 3 * (size_t)n_prob)) return fail(ctx, FQ_E_ARG, "limits must be > 0");
   FQ_CUDA(cudaSetDevice(ctx->device));
   FQ_CUDA(ctx->d_in.reserve(L.in_bytes));
   FQ_CUDA(ctx->d_out.reserve(L.out_bytes));
@@ -394,6 +415,9 @@ extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double
   if (n_sigma > (1 << 20)) return fail(ctx, FQ_E_ARG, "n_sigma > 2^20");
   const int ne = force_final ? 3 : 2;
   if (N < ne || N > FQ_MAX_N) return fail(ctx, FQ_E_ARG, "N out of range");
+  if (!all_finite(x0, 9) || !all_finite(xf, 9) || !all_positive_finite(lim, 3) || !all_positive_finite(dts, (size_t)n_dt) ||
+      (P > 0 && !all_finite(Ab, 4 * (size_t)face_ofs[P])))
+    return fail(ctx, FQ_E_ARG, "non-finite input, dt <= 0 or limit <= 0");
   const long long n_cand_ll = (long long)n_dt * n_sigma;
   if (n_cand_ll > (1LL << 30)) return fail(ctx, FQ_E_ARG, "too many candidates");
   const int n_cand = (int)n_cand_ll;

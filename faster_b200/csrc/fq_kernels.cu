@@ -297,7 +297,8 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
         recompute_Y(a, TZ, m, lane);
         break;
       }
-      // partial step: active row l leaves
+      // partial step: active row l leaves.  (l < 0 here means t1/t2 are NaN -- non-finite input: give up)
+      if (l < 0) { status = -1; done = true; break; }
       if (!dep)
         for (int j = lane; j < nw; j += 32) m.w[j] = fma(t1, m.z[j], m.w[j]);
       for (int k = lane; k < q; k += 32) m.lam[k] = fma(-t1, m.r[k], m.lam[k]);

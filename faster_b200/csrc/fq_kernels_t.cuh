@@ -498,7 +498,8 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
         update_Y<D>(m, TZ, Yeq, bthr, SY, lane, bkey, bcode);
         break;
       }
-      // ---- partial step: active element l leaves
+      // ---- partial step: active element l leaves.  (l < 0 here means t1/t2 are NaN -- non-finite input: give up)
+      if (l < 0) { status = -1; break; }
 #pragma unroll
       for (int s = 0; s < SLOTS; s++)
       {

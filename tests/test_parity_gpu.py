@@ -385,3 +385,52 @@ def test_throughput_copy_path_matches_latency_path(solver):
         a, b = cand_ofs[k], cand_ofs[k + 1]
         f1, c1, _, _ = solver.solve_batch(N, probs[k]["x0"], probs[k]["xf"], probs[k]["lim"], probs[k]["polys"], dts[k], sigs[k])
         assert np.array_equal(f_big[a:b], f1) and np.array_equal(c_big[a:b], c1)
+
+
+def test_non_finite_inputs_are_rejected_or_survive(solver):
+    """NaN / Inf / non-positive dt: the host-pointer entries refuse them; the device-pointer entry cannot look at the
+    data, so the kernels must come back (numeric failure -> infeasible) instead of faulting."""
+    import torch
+    pb = cr.make_corridor(31, 3, 10)
+    sig = cr.monotone_sigmas(10, 3)[:8]
+    for bad_dt in (np.nan, np.inf, 0.0, -0.3):
+        d = np.full(8, 0.5)
+        d[3] = bad_dt
+        with pytest.raises(capi.FqError):
+            solver.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], d, sig)
+    x0 = pb["x0"].copy()
+    x0[4] = np.nan
+    with pytest.raises(capi.FqError):
+        solver.solve_batch(10, x0, pb["xf"], pb["lim"], pb["polys"], np.full(8, 0.5), sig)
+    with pytest.raises(capi.FqError):
+        solver.gen_new_traj(10, x0, pb["xf"], pb["lim"], pb["polys"], np.arange(1, 4) * 0.3, sig)
+    # device-pointer entry with poisoned data: must terminate and flag everything infeasible
+    dev = torch.device("cuda", 0)
+    P, fo, Ab = capi.pack_polys(pb["polys"])
+    for poison in ("dt", "x0", "Ab"):
+        for generic in (0, 1):
+            solver.set_option("force_generic_kernel", generic)
+            dts = np.full(8, 0.5)
+            x0 = pb["x0"].copy()
+            Abp = Ab.copy()
+            if poison == "dt":
+                dts[:] = [np.nan, np.inf, 0.0, -1.0, np.nan, 1e308, 1e-308, np.nan]
+            elif poison == "x0":
+                x0[0] = np.nan
+            else:
+                Abp[2, 1] = np.inf
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            d = dict(x0=t(x0), xf=t(pb["xf"]), lim=t(pb["lim"]), po=t(np.array([0, P], np.int32)), fo=t(fo), Ab=t(Abp),
+                     co=t(np.array([0, 8], np.int32)), dt=t(dts), sg=t(sig))
+            feas = torch.ones(8, dtype=torch.uint8, device=dev)
+            cost = torch.zeros(8, dtype=torch.float64, device=dev)
+            solver.solve_multi_dev(10, True, 1, d["x0"].data_ptr(), d["xf"].data_ptr(), d["lim"].data_ptr(),
+                                   d["po"].data_ptr(), d["fo"].data_ptr(), d["Ab"].data_ptr(), d["co"].data_ptr(), 8,
+                                   int(fo[-1]), d["dt"].data_ptr(), d["sg"].data_ptr(), feas.data_ptr(), cost.data_ptr())
+            torch.cuda.synchronize()
+            f = feas.cpu().numpy()
+            if poison == "dt":
+                assert not f[[0, 1, 2, 3, 4, 7]].any()
+            else:
+                assert not f.any()
+    solver.set_option("force_generic_kernel", 0)
