@@ -120,20 +120,30 @@ void fill_plan_args(const PlanDev& pd, FqKernelArgs* a)
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// branch-free scans (vectorise): x - x == 0 iff x is finite
+// branch-free integer scans over the bit patterns (these vectorise; floating-point reductions would not)
 inline bool all_finite(const double* p, size_t n)
 {
   if (!p) return n == 0;
-  double acc = 0;
-  for (size_t i = 0; i < n; i++) acc += (p[i] - p[i]) * (p[i] - p[i]);
-  return acc == 0;
+  uint64_t bad = 0;
+  for (size_t i = 0; i < n; i++)
+  {
+    uint64_t b;
+    std::memcpy(&b, p + i, sizeof(b));
+    bad |= (uint64_t)(((b >> 52) & 0x7ffu) == 0x7ffu);        // exponent all ones: Inf or NaN
+  }
+  return bad == 0;
 }
 inline bool all_positive_finite(const double* p, size_t n)
 {
-  if (!all_finite(p, n)) return false;
-  double mn = 1.0;
-  for (size_t i = 0; i < n; i++) mn = p[i] < mn ? p[i] : mn;
-  return mn > 0;
+  if (!p) return n == 0;
+  uint64_t bad = 0;
+  for (size_t i = 0; i < n; i++)
+  {
+    uint64_t b;
+    std::memcpy(&b, p + i, sizeof(b));
+    bad |= (uint64_t)(((b >> 52) & 0x7ffu) == 0x7ffu) | (b >> 63) | (uint64_t)((b << 1) == 0);   // Inf/NaN, negative, +-0
+  }
+  return bad == 0;
 }
 }  // namespace
 

@@ -108,7 +108,7 @@ __device__ __forceinline__ void drop_row(const FqKernelArgs& a, const WarpMem& m
 }
 
 __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const double* T0, const double* sAb,
-                                const int* sfo, const WarpMem& m, int prob, int cand, int lane)
+                                const int* sfo, const WarpMem& m, int prob, int cand, int lane, bool rows_bad)
 {
   const int N = a.N, nz = a.nz, nw = a.nw, NY = a.NY, ld = a.ld, ne = a.ne;
   const double dt = a.dt[cand], dt2 = dt * dt;
@@ -164,6 +164,23 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
   __syncwarp();
 
   int q = 0, status = -1, it = 0;
+  { // non-finite / non-positive inputs (unvalidated device-pointer entry): report "not solved", never fault
+    bool okc = dt > 0 && dt < 1e100 && lim0 > 0 && lim0 < 1e300 && lim1 > 0 && lim1 < 1e300 && lim2 > 0 && lim2 < 1e300 &&
+               !rows_bad;
+    for (int idx = lane; idx < 3 * NY; idx += 32) okc = okc && fabs(m.Yeq[idx]) < 1e300;
+    if (!__all_sync(FULL, okc))
+    {
+      if (lane == 0)
+      {
+        a.feasible[cand] = 0;
+        a.cost[cand] = INFINITY;
+        if (a.iters) a.iters[cand] = -1;
+      }
+      if (a.coeffs)
+        for (int idx = lane; idx < 12 * N; idx += 32) a.coeffs[(size_t)cand * N * 12 + idx] = 0.0;
+      return;
+    }
+  }
   for (;;)
   {
     // ================= most violated row =================
@@ -368,13 +385,20 @@ __global__ void __launch_bounds__(W * 32) fq_solve_kernel(const FqKernelArgs a, 
   const int p0 = a.poly_ofs[prob], P = a.poly_ofs[prob + 1] - p0;
   const int f0 = a.face_ofs[p0];
   const int nf = P > 0 ? a.face_ofs[p0 + P] - f0 : 0;
+  bool rows_bad = false;
   {
     const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
     double2* dst = reinterpret_cast<double2*>(sAb);
-    for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x) dst[i] = src[i];
+    int bad = 0;
+    for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x)
+    {
+      const double2 v = src[i];
+      bad |= !(fabs(v.x) < 1e300) || !(fabs(v.y) < 1e300);
+      dst[i] = v;
+    }
     for (int i = threadIdx.x; i <= P && i < 36; i += blockDim.x) sfo[i] = a.face_ofs[p0 + i] - f0;
+    rows_bad = __syncthreads_or(bad) != 0;
   }
-  __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cand = first + warp;
@@ -396,7 +420,7 @@ __global__ void __launch_bounds__(W * 32) fq_solve_kernel(const FqKernelArgs a, 
   m.hdr = p;
   int* ip = ibase + warp * per_warp_ints();
   m.seg_ofs = ip; m.sig = ip + FQ_MAX_N + 2;
-  solve_candidate(a, TZ, T0, sAb, sfo, m, prob, cand, lane);
+  solve_candidate(a, TZ, T0, sAb, sfo, m, prob, cand, lane, rows_bad);
 }
 
 // genNewTraj selection (solverGurobi.cpp:445-472): first dt with a feasible assignment, then min cost.

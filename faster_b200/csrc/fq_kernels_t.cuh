@@ -200,7 +200,7 @@ template <class D>
 __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict__ TZ,
                                 const double* __restrict__ SY, const double* __restrict__ sAb,
                                 const int* __restrict__ sfo, const WarpState<D>& m, int* __restrict__ seg_ofs,
-                                int prob, int cand, int lane)
+                                int prob, int cand, int lane, bool rows_bad)
 {
   constexpr int N = D::N, NZ = D::NZ, NW = D::NW, NY = D::NY, NYP = D::NYP, LD = D::LD, NE = D::NE, SLOTS = D::SLOTS;
   const double dt = a.dt[cand], dt2 = dt * dt;
@@ -249,6 +249,28 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
           for (int ax = 0; ax < 3; ax++) Yeq[r][ax] = fma(t, hdr[ax][k], Yeq[r][ax]);
         }
       }
+    }
+  }
+  // ---- non-finite or non-positive inputs (the device-pointer entry cannot be validated on the host): such a
+  //      candidate is reported "not solved" right away.  NaN keys would otherwise rank as "satisfied".
+  {
+    bool okc = dt > 0 && dt < 1e100 && lim0 > 0 && lim0 < 1e300 && lim1 > 0 && lim1 < 1e300 && lim2 > 0 && lim2 < 1e300 &&
+               !rows_bad;
+#pragma unroll
+    for (int r = 0; r < D::RPL; r++)
+#pragma unroll
+      for (int ax = 0; ax < 3; ax++) okc = okc && fabs(Yeq[r][ax]) < 1e300;
+    if (!__all_sync(FULL, okc))
+    {
+      if (lane == 0)
+      {
+        a.feasible[cand] = 0;
+        a.cost[cand] = INFINITY;
+        if (a.iters) a.iters[cand] = -1;
+      }
+      if (a.coeffs)
+        for (int idx = lane; idx < 12 * N; idx += 32) a.coeffs[(size_t)cand * N * 12 + idx] = 0.0;
+      return;
     }
   }
   // ---- corridor item list: item = t << 12 | need_cp0 << 11 | face (row of the staged Ab)
@@ -631,25 +653,28 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <
     const int p0 = a.poly_ofs[prob], P = a.poly_ofs[prob + 1] - p0;
     const int f0 = a.face_ofs[p0];
     const int nf = P > 0 ? a.face_ofs[p0 + P] - f0 : 0;
+    bool rows_bad = false;
     {
       const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
       double2* dst = reinterpret_cast<double2*>(sAb);
+      int bad = 0;
       for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x)
       {
         double2 v = src[i];
+        bad |= !(fabs(v.x) < 1e300) || !(fabs(v.y) < 1e300);
         if (i & 1) v.y += FQ_ROW_TOL;              // rows are staged as [Ax Ay Az b+tol]
         dst[i] = v;
       }
       for (int i = threadIdx.x; i <= P && i < 36; i += blockDim.x) sfo[i] = a.face_ofs[p0 + i] - f0;
+      rows_bad = __syncthreads_or(bad) != 0;       // also the barrier that publishes the staged rows
     }
-    __syncthreads();
     for (;;)
     {
       int c = 0;
       if (lane == 0) c = atomicAdd(counters + prob, 1);
       c = __shfl_sync(FULL, c, 0);
       if (c >= count) break;
-      solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, c_begin + c, lane);
+      solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, c_begin + c, lane, rows_bad);
     }
     __syncthreads();                               // everyone is done with the staged rows
   }
