@@ -4,6 +4,7 @@
 #include "fq_plan.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -59,7 +60,8 @@ std::string g_create_error;
 struct fq_ctx
 {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev_head = nullptr;
   std::map<int, PlanDev> plans;   // key N*2+force_final
   Arena d_in, d_out;
   PinnedArena h_in, h_out;
@@ -120,31 +122,8 @@ void fill_plan_args(const PlanDev& pd, FqKernelArgs* a)
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// branch-free integer scans over the bit patterns (these vectorise; floating-point reductions would not)
-inline bool all_finite(const double* p, size_t n)
-{
-  if (!p) return n == 0;
-  uint64_t bad = 0;
-  for (size_t i = 0; i < n; i++)
-  {
-    uint64_t b;
-    std::memcpy(&b, p + i, sizeof(b));
-    bad |= (uint64_t)(((b >> 52) & 0x7ffu) == 0x7ffu);        // exponent all ones: Inf or NaN
-  }
-  return bad == 0;
-}
-inline bool all_positive_finite(const double* p, size_t n)
-{
-  if (!p) return n == 0;
-  uint64_t bad = 0;
-  for (size_t i = 0; i < n; i++)
-  {
-    uint64_t b;
-    std::memcpy(&b, p + i, sizeof(b));
-    bad |= (uint64_t)(((b >> 52) & 0x7ffu) == 0x7ffu) | (b >> 63) | (uint64_t)((b << 1) == 0);   // Inf/NaN, negative, +-0
-  }
-  return bad == 0;
-}
+inline bool all_finite(const double* p, size_t n) { return fq_scan_all_finite(p, n); }
+inline bool all_positive_finite(const double* p, size_t n) { return fq_scan_all_positive_finite(p, n); }
 }  // namespace
 
 extern "C" int fq_create(fq_ctx** out, int device)
@@ -162,6 +141,8 @@ extern "C" int fq_create(fq_ctx** out, int device)
   ctx->device = device;
   e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_head, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   ctx->counters_cap = 4096;
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counters, sizeof(int) * (size_t)kCounterSlots * ctx->counters_cap);
@@ -182,6 +163,8 @@ extern "C" void fq_destroy(fq_ctx* ctx)
   for (auto& kv : ctx->plans) { cudaFree(kv.second.TZ); cudaFree(kv.second.T0); cudaFree(kv.second.FT); }
   ctx->d_in.release(); ctx->d_out.release(); ctx->h_in.release(); ctx->h_out.release();
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->ev_head) cudaEventDestroy(ctx->ev_head);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -280,11 +263,8 @@ int describe(fq_ctx* ctx, int N, int force_final, int n_prob, const int* poly_of
     }
     if (P > 0 && sigma)
     { // branch-free max over the bytes (vectorises); one compare per problem
-      const uint8_t* sp = sigma + (size_t)cand_ofs[j] * N;
-      const size_t cnt = (size_t)nc * N;
-      unsigned mx = 0;
-      for (size_t i = 0; i < cnt; i++) mx = sp[i] > mx ? sp[i] : mx;
-      if ((int)mx >= P) return fail(ctx, FQ_E_ARG, "sigma entry >= number of polytopes");
+      if (fq_scan_max_u8(sigma + (size_t)cand_ofs[j] * N, (size_t)nc * N) >= P)
+        return fail(ctx, FQ_E_ARG, "sigma entry >= number of polytopes");
     }
     if (nc > *max_cand) *max_cand = nc;
     if (nf > *max_faces) *max_faces = nf;
@@ -313,12 +293,30 @@ int describe(fq_ctx* ctx, int N, int force_final, int n_prob, const int* poly_of
 constexpr size_t kPackThreshold = 512 * 1024;   // below this, inputs are packed into one pinned staging copy
 }  // namespace
 
+namespace
+{
+struct Trace
+{ // FQ_TRACE=1: host-side phase times of fq_solve_multi on stderr
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  Trace() : on(std::getenv("FQ_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what)
+  {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[fq trace] %-10s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf,
                               const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
                               const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible,
                               double* cost, double* coeffs, int32_t* iters)
 {
   if (!ctx) return FQ_E_ARG;
+  Trace tr;
   if (!x0 || !xf || !lim || !poly_ofs || !face_ofs || !cand_ofs || !dt || !feasible || !cost)
     return fail(ctx, FQ_E_ARG, "NULL argument");
   HostLayout L;
@@ -326,6 +324,7 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
   int rc = describe(ctx, N, force_final, n_prob, poly_ofs, face_ofs, cand_ofs, sigma, coeffs != nullptr,
                     iters != nullptr, &L, &n_cand, &n_poly, &n_face, &max_cand, &max_faces, &max_poly_faces);
   if (rc) return rc;
+  tr.mark("describe");
   if (n_cand == 0) return 0;
   if (n_poly > 0 && (!Ab || !sigma)) return fail(ctx, FQ_E_ARG, "polytopes given but Ab or sigma is NULL");
   if (!all_finite(x0, 9 * (size_t)n_prob) || !all_finite(xf, 9 * (size_t)n_prob) || !all_finite(lim, 3 * (size_t)n_prob) ||
@@ -333,6 +332,7 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
     return fail(ctx, FQ_E_ARG, "non-finite value in x0/xf/lim/Ab");
   if (!all_positive_finite(dt, (size_t)n_cand)) return fail(ctx, FQ_E_ARG, "dt must be finite and > 0");
   if (!all_positive_finite(lim, 3 * (size_t)n_prob)) return fail(ctx, FQ_E_ARG, "limits must be > 0");
+  tr.mark("finite");
   FQ_CUDA(cudaSetDevice(ctx->device));
   FQ_CUDA(ctx->d_in.reserve(L.in_bytes));
   FQ_CUDA(ctx->d_out.reserve(L.out_bytes));
@@ -356,17 +356,64 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
     FQ_CUDA(cudaMemcpyAsync(din, ctx->h_in.p, L.in_bytes, cudaMemcpyHostToDevice, st));
   }
   else
-  { // throughput path: the per-candidate arrays (dt, sigma) are DMA'd straight from the caller's buffers (true
-    // async when they are pinned); the per-problem description is small and goes through one staged copy
+  { // throughput path: the per-problem description is small and goes through one staged copy; the per-candidate arrays
+    // (dt, sigma) are DMA'd straight from the caller's buffers (true async when they are pinned) in up to four slices
+    // of whole problems, alternating between two streams: slice k+1 uploads while slice k computes and slice k-1
+    // downloads, and the next slice's CTAs fill the SMs that the previous launch's tail leaves idle.
     const bool pack_head = L.dt <= kPackThreshold;
     if (pack_head) FQ_CUDA(ctx->h_in.reserve(L.dt));
     for (const Piece& p : pieces)
     {
-      if (!p.bytes) continue;
-      if (pack_head && p.off < L.dt) std::memcpy((char*)ctx->h_in.p + p.off, p.src, p.bytes);
+      if (!p.bytes || p.off >= L.dt) continue;
+      if (pack_head) std::memcpy((char*)ctx->h_in.p + p.off, p.src, p.bytes);
       else FQ_CUDA(cudaMemcpyAsync(din + p.off, p.src, p.bytes, cudaMemcpyHostToDevice, st));
     }
     if (pack_head) FQ_CUDA(cudaMemcpyAsync(din, ctx->h_in.p, L.dt, cudaMemcpyHostToDevice, st));
+    FQ_CUDA(cudaEventRecord(ctx->ev_head, st));
+    FQ_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_head, 0));
+    const int n_slices = n_prob < 4 ? n_prob : 4;
+    int p_lo = 0;
+    for (int k = 0; k < n_slices; k++)
+    {
+      // slice boundaries balance the candidate counts
+      const long long target = (long long)n_cand * (k + 1) / n_slices;
+      int p_hi = p_lo;
+      while (p_hi < n_prob && (cand_ofs[p_hi + 1] <= target || p_hi == p_lo)) p_hi++;
+      if (k == n_slices - 1) p_hi = n_prob;
+      if (p_hi == p_lo) continue;
+      const size_t c_lo = (size_t)cand_ofs[p_lo], c_n = (size_t)cand_ofs[p_hi] - c_lo;
+      cudaStream_t s2 = (k & 1) ? ctx->stream2 : st;
+      int mc = 0;
+      for (int j = p_lo; j < p_hi; j++) mc = std::max(mc, cand_ofs[j + 1] - cand_ofs[j]);
+      if (c_n > 0)
+      {
+        FQ_CUDA(cudaMemcpyAsync(din + L.dt + sizeof(double) * c_lo, dt + c_lo, sizeof(double) * c_n, cudaMemcpyHostToDevice, s2));
+        if (n_poly > 0)
+          FQ_CUDA(cudaMemcpyAsync(din + L.sigma + c_lo * N, sigma + c_lo * N, c_n * N, cudaMemcpyHostToDevice, s2));
+        else
+          FQ_CUDA(cudaMemsetAsync(din + L.sigma + c_lo * N, 0, c_n * N, s2));
+        rc = launch_solve(ctx, N, force_final, p_hi - p_lo, (const double*)(din + L.x0) + 9 * (size_t)p_lo,
+                          (const double*)(din + L.xf) + 9 * (size_t)p_lo, (const double*)(din + L.lim) + 3 * (size_t)p_lo,
+                          (const int*)(din + L.poly_ofs) + p_lo, (const int*)(din + L.face_ofs), (const double*)(din + L.Ab),
+                          (const int*)(din + L.cand_ofs) + p_lo, mc, max_faces, max_poly_faces, (const double*)(din + L.dt),
+                          (const uint8_t*)(din + L.sigma), (uint8_t*)(dout + L.feasible), (double*)(dout + L.cost),
+                          coeffs ? (double*)(dout + L.coeffs) : nullptr, iters ? (int32_t*)(dout + L.iters) : nullptr, s2);
+        if (rc) { cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->stream2); return rc; }
+        FQ_CUDA(cudaMemcpyAsync(cost + c_lo, dout + L.cost + sizeof(double) * c_lo, sizeof(double) * c_n, cudaMemcpyDeviceToHost, s2));
+        FQ_CUDA(cudaMemcpyAsync(feasible + c_lo, dout + L.feasible + c_lo, c_n, cudaMemcpyDeviceToHost, s2));
+        if (coeffs)
+          FQ_CUDA(cudaMemcpyAsync(coeffs + 12 * (size_t)N * c_lo, dout + L.coeffs + sizeof(double) * 12 * (size_t)N * c_lo,
+                                  sizeof(double) * 12 * (size_t)N * c_n, cudaMemcpyDeviceToHost, s2));
+        if (iters)
+          FQ_CUDA(cudaMemcpyAsync(iters + c_lo, dout + L.iters + sizeof(int32_t) * c_lo, sizeof(int32_t) * c_n, cudaMemcpyDeviceToHost, s2));
+      }
+      p_lo = p_hi;
+    }
+    tr.mark("enqueue");
+    FQ_CUDA(cudaStreamSynchronize(ctx->stream2));
+    FQ_CUDA(cudaStreamSynchronize(st));
+    tr.mark("wait");
+    return 0;
   }
   if (n_poly == 0) FQ_CUDA(cudaMemsetAsync(din + L.sigma, 0, sig_bytes, st));
   rc = launch_solve(ctx, N, force_final, n_prob, (const double*)(din + L.x0), (const double*)(din + L.xf),

@@ -283,3 +283,41 @@ extern "C" int fq_plan_tables(int N, int force_final, double* TZ, double* T0, do
   if (FT) std::memcpy(FT, p.FT.data(), sizeof(double) * p.FT.size());
   return p.NY;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Input validation scans used by the host-pointer entry points (fq_capi.cu).  Integer-only bodies so that they
+// vectorise; compiled twice (AVX2 / baseline) with run-time dispatch -- a 65 536-candidate batch must not spend
+// longer being validated than being copied.
+// ---------------------------------------------------------------------------------------------------------
+#if defined(__x86_64__) && defined(__GNUC__)
+#define FQ_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define FQ_CLONES
+#endif
+
+FQ_CLONES bool fq_scan_all_finite(const double* p, size_t n)
+{
+  if (!p) return n == 0;
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(p);
+  uint64_t bad = 0;
+  for (size_t i = 0; i < n; i++) bad |= (uint64_t)((w[i] & 0x7ff0000000000000ull) == 0x7ff0000000000000ull);
+  return bad == 0;
+}
+
+FQ_CLONES bool fq_scan_all_positive_finite(const double* p, size_t n)
+{
+  if (!p) return n == 0;
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(p);
+  uint64_t bad = 0;
+  for (size_t i = 0; i < n; i++)
+    bad |= (uint64_t)((w[i] & 0x7ff0000000000000ull) == 0x7ff0000000000000ull) | (w[i] >> 63) | (uint64_t)((w[i] << 1) == 0);
+  return bad == 0;
+}
+
+FQ_CLONES int fq_scan_max_u8(const uint8_t* p, size_t n)
+{
+  uint8_t mx = 0;
+  for (size_t i = 0; i < n; i++) mx = p[i] > mx ? p[i] : mx;
+  return mx;
+}

@@ -34,3 +34,10 @@ struct FqPlanHost
 
 // returns false for unsupported N
 bool fq_build_plan(int N, int force_final, FqPlanHost* plan);
+
+// validation scans (fq_host.cpp)
+#include <cstddef>
+#include <cstdint>
+bool fq_scan_all_finite(const double* p, size_t n);
+bool fq_scan_all_positive_finite(const double* p, size_t n);
+int fq_scan_max_u8(const uint8_t* p, size_t n);

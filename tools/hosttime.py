@@ -1,4 +1,4 @@
-import sys, time, numpy as np
+import os, sys, time, numpy as np
 sys.path.insert(0,'.')
 import bench
 from faster_b200 import capi
