@@ -465,6 +465,7 @@ extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double
                                int* sigma_index, double* cost, double* coeffs)
 {
   if (!ctx) return FQ_E_ARG;
+  Trace tr;
   if (!x0 || !xf || !lim || !dts) return fail(ctx, FQ_E_ARG, "NULL argument");
   if (P < 0 || P > FQ_MAX_POLY || n_dt <= 0) return fail(ctx, FQ_E_ARG, "bad P or n_dt");
   if (P == 0) n_sigma = 1;
@@ -527,6 +528,7 @@ extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double
     int* fo = (int*)(hi + ofo); fo[0] = 0; for (int p = 0; p < P; p++) fo[p + 1] = face_ofs[p + 1];
     int* co = (int*)(hi + oco); co[0] = 0; co[1] = n_cand;
   }
+  tr.mark("pack");
   cudaStream_t st = ctx->stream;
   char* din = (char*)ctx->d_in.p;
   char* dout = (char*)ctx->d_out.p;
@@ -546,7 +548,9 @@ extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double
   char* ho = (char*)ctx->h_out.p;
   const size_t win_bytes = sizeof(double) * (1 + 12 * (size_t)N);
   FQ_CUDA(cudaMemcpyAsync(ho, dout + owin, win_bytes + 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  tr.mark("enqueue");
   FQ_CUDA(cudaStreamSynchronize(st));
+  tr.mark("wait");
   static_assert(sizeof(double) == 8, "layout");
   const int* idx = (const int*)(ho + win_bytes);
   const double* win = (const double*)ho;

@@ -236,3 +236,22 @@ def test_oracle_multi_equals_batches(oracle):
         fo, co_, _ = oracle.solve_batch(N, p["x0"], p["xf"], p["lim"], p["polys"], dts[k], sigs[k], True)
         a, b = cand_ofs[k], cand_ofs[k + 1]
         assert np.array_equal(f[a:b], fo) and np.array_equal(c[a:b], co_)
+
+
+def test_oracle_reproduces_committed_goldens(oracle, demo_corridor):
+    """tests/golden/corridor_continuous_expected.json (generated once, HiGHS-cross-checked) pins the oracle across rounds."""
+    import json
+    import os
+    exp = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "corridor_continuous_expected.json")))
+    fx = demo_corridor
+    sig = np.array(exp["sigmas"], np.uint8)
+    for dt, fe, ce in zip(exp["dts"], exp["feasible"], exp["cost"]):
+        f, c, _ = oracle.solve_batch(fx["N"], fx["x0"], fx["xf"], fx["lim"], fx["polys"], np.full(len(sig), dt), sig, True, threads=4)
+        assert f.tolist() == fe
+        for k, v in enumerate(ce):
+            if v is not None:
+                assert abs(c[k] - v) <= 1e-9 * max(1.0, v)
+    g = oracle.gen_new_traj(fx["N"], fx["x0"], fx["xf"], fx["lim"], fx["polys"], 0.01, 1.0, 10.0, 1.0, None, True)
+    e = exp["gen_new_traj"]
+    assert g["solved"] == e["solved"] and g["factor"] == e["factor"] and g["trials"] == e["trials"]
+    assert abs(g["dt"] - e["dt"]) <= 1e-15 and abs(g["cost"] - e["cost"]) <= 1e-9 * e["cost"]

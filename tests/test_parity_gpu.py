@@ -434,3 +434,26 @@ def test_non_finite_inputs_are_rejected_or_survive(solver):
             else:
                 assert not f.any()
     solver.set_option("force_generic_kernel", 0)
+
+
+def test_cuda_reproduces_committed_goldens(solver, demo_corridor):
+    """CUDA path against the committed golden vectors (tests/golden/corridor_continuous_expected.json)."""
+    import json
+    import os
+    exp = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "corridor_continuous_expected.json")))
+    fx = demo_corridor
+    sig = np.array(exp["sigmas"], np.uint8)
+    for dt, fe, ce in zip(exp["dts"], exp["feasible"], exp["cost"]):
+        f, c, co, _ = solver.solve_batch(fx["N"], fx["x0"], fx["xf"], fx["lim"], fx["polys"], np.full(len(sig), dt), sig, True, True)
+        assert f.tolist() == fe
+        for k, v in enumerate(ce):
+            if v is not None:
+                assert abs(c[k] - v) <= REL * max(1.0, v)
+        key = "%g" % dt
+        if key in exp["best_coeffs"]:
+            b = exp["best_coeffs"][key]
+            assert np.abs(co[b["sigma_index"]] - np.array(b["coeffs"])).max() <= 1e-6
+    e = exp["gen_new_traj"]
+    dti = capi.dt_initial(fx["x0"], fx["xf"], fx["lim"], fx["N"])
+    g = solver.gen_new_traj(fx["N"], fx["x0"], fx["xf"], fx["lim"], fx["polys"], np.arange(1.0, 11.0) * max(dti, 0.02), sig, True)
+    assert g["solved"] == e["solved"] and g["dt_index"] + 1 == e["trials"] and abs(g["cost"] - e["cost"]) <= REL * e["cost"]
