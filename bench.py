@@ -315,6 +315,11 @@ def main():
                     "issue_active_pct": float(np.mean([l["issue_active_pct"] for l in ls])),
                     "warp_instructions_per_candidate": float(np.mean([l["warp_instructions"] for l in ls]) / n_cand),
                     "source": pj["label"]}
+            if all("fp64_flops" in l for l in ls):
+                # executed FP64 flops per launch (ncu counters) over the live launch time, against the NOMINAL FP64 peak
+                fl = float(np.mean([l["fp64_flops"] for l in ls]))
+                prof["fp64"] = {"flops_per_launch": fl, "achieved_tflops": fl / (kernel_ms * 1e-3) / 1e12,
+                                "peak_tflops_nominal": 37.2, "frac": fl / (kernel_ms * 1e-3) / 1e12 / 37.2}
         except Exception:
             pass
         h2d = sum(int(h[k].numel() * h[k].element_size()) for h in host for k in keys)
