@@ -365,7 +365,14 @@ def main():
                               "against": "oracle/fq_oracle.c (CPU restatement), same inputs"}
             threads = os.cpu_count() or 1
             rate, sample = cpu_reference_rate(max(4, threads // 4), threads, args.cpu_seconds)
-            line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample}
+            # the robot's view on the CPU: one sequential genNewTraj sweep with branch-and-bound over all assignments
+            lat_cpu = []
+            for _ in range(15):
+                t0 = time.perf_counter()
+                po.gen_new_traj(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], pb["DC"], 1.0, 10.0, 1.0, None, True)
+                lat_cpu.append(time.perf_counter() - t0)
+            line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample,
+                                    "replan_latency_us": float(np.median(lat_cpu) * 1e6)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -8,7 +8,7 @@
 //   fillX()       samples the solution every DC seconds into X_temp_ (:122-168)
 // What differs:  one GPU launch evaluates every (factor x assignment) candidate of the sweep at once instead of one
 // Gurobi MIQP per factor; the binaries b[t][p] (:217-246) are enumerated as interval->polytope assignments
-// (non-decreasing ones by default, see setAssignmentMode).  Methods that returned GRBLinExpr return the value of
+// (all P^N of them while that is small -- the exact MIQP --, the non-decreasing ones beyond; see setAssignmentMode).  Methods that returned GRBLinExpr return the value of
 // that expression at the current solution.  Additive: getCoeffs(), getCost(), getAssignment().
 // Header-only; link with -lfaster_b200.  No Gurobi, no CPU fallback: if no GPU/context can be created genNewTraj()
 // returns false and prints the reason (the reference's behaviour for every non-OPTIMAL status, :580-648).
@@ -46,7 +46,7 @@ public:
 class SolverGurobi
 {
 public:
-  enum AssignmentMode { MONOTONE = 0, ALL = 1 };
+  enum AssignmentMode { MONOTONE = 0, ALL = 1, AUTO = 2 };
 
   SolverGurobi()
   {
@@ -75,7 +75,16 @@ public:
   void setWMax(double w) { w_max_ = w; }                                         // :489-492
   void setMode(int mode) { mode_ = mode; }                                       // :65-68
   void setDevice(int device) { device_ = device; }                               // additive: CUDA device index
-  void setAssignmentMode(AssignmentMode m, long max_assignments = 16384) { amode_ = m; max_sigma_ = max_assignments; }
+  // Which interval->polytope assignments are evaluated for every time allocation:
+  //   ALL       every one of the P^N (the exact MIQP optimum, like Gurobi's branch-and-bound);
+  //   MONOTONE  the non-decreasing ones only, C(N+P-1, P-1) (identical genNewTraj results in 960/960 measured sweeps,
+  //             see DESIGN.md section 2);
+  //   AUTO      (default) ALL while P^N <= auto_all_limit (4096: covers the shipped yaml, N=6 and <=3 polytopes: 729),
+  //             MONOTONE beyond.
+  void setAssignmentMode(AssignmentMode m, long max_assignments = 16384, long auto_all_limit = 4096)
+  {
+    amode_ = m; max_sigma_ = max_assignments; auto_all_limit_ = auto_all_limit;
+  }
 
   void setX0(state& d)                                                           // :298-313
   {
@@ -266,7 +275,9 @@ protected:
     if (P_ == 0) { sigmas_.clear(); n_sigma_ = 1; return true; }
     if (sig_N_ == N_ && sig_P_ == P_ && sig_mode_ == amode_) return true;
     sigmas_.clear();
-    if (amode_ == MONOTONE)
+    AssignmentMode mode = amode_;
+    if (mode == AUTO) mode = std::pow((double)P_, (double)N_) <= (double)auto_all_limit_ ? ALL : MONOTONE;
+    if (mode == MONOTONE)
     {
       const long total = fq_monotone_sigmas(N_, P_, nullptr, 0);
       std::vector<uint8_t> all((size_t)total * N_);
@@ -311,9 +322,9 @@ protected:
   std::vector<double> Ab_;           // rows [Ax Ay Az b]
   std::vector<double> coeffs_;       // N x 12
   std::vector<uint8_t> sigmas_;
-  long n_sigma_ = 1, max_sigma_ = 16384;
+  long n_sigma_ = 1, max_sigma_ = 16384, auto_all_limit_ = 4096;
   int sig_N_ = -1, sig_P_ = -1, sig_mode_ = -1, sigma_idx_ = -1;
-  AssignmentMode amode_ = MONOTONE;
+  AssignmentMode amode_ = AUTO;
   fq_ctx* ctx_ = nullptr;
   int device_ = 0;
   int verbose_ = 0;
