@@ -327,12 +327,18 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
   tr.mark("describe");
   if (n_cand == 0) return 0;
   if (n_poly > 0 && (!Ab || !sigma)) return fail(ctx, FQ_E_ARG, "polytopes given but Ab or sigma is NULL");
-  if (!all_finite(x0, 9 * (size_t)n_prob) || !all_finite(xf, 9 * (size_t)n_prob) || !all_finite(lim, 3 * (size_t)n_prob) ||
-      !all_finite(Ab, 4 * (size_t)n_face))
-    return fail(ctx, FQ_E_ARG, "non-finite value in x0/xf/lim/Ab");
-  if (!all_positive_finite(dt, (size_t)n_cand)) return fail(ctx, FQ_E_ARG, "dt must be finite and > 0");
-  if (!all_positive_finite(lim, 3 * (size_t)n_prob)) return fail(ctx, FQ_E_ARG, "limits must be > 0");
-  tr.mark("finite");
+  // value checks (the kernels also refuse non-finite data, but an argument error is the better answer).  Small batches:
+  // before anything is enqueued.  Large batches: while the GPU already works on the data (see the throughput path).
+  auto values_ok = [&]() -> const char* {
+    if (!all_finite(x0, 9 * (size_t)n_prob) || !all_finite(xf, 9 * (size_t)n_prob) || !all_finite(Ab, 4 * (size_t)n_face))
+      return "non-finite value in x0/xf/Ab";
+    if (!all_positive_finite(dt, (size_t)n_cand)) return "dt must be finite and > 0";
+    if (!all_positive_finite(lim, 3 * (size_t)n_prob)) return "limits must be finite and > 0";
+    return nullptr;
+  };
+  const bool big = L.in_bytes > kPackThreshold;
+  if (!big)
+    if (const char* why = values_ok()) return fail(ctx, FQ_E_ARG, why);
   FQ_CUDA(cudaSetDevice(ctx->device));
   FQ_CUDA(ctx->d_in.reserve(L.in_bytes));
   FQ_CUDA(ctx->d_out.reserve(L.out_bytes));
@@ -410,9 +416,12 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
       p_lo = p_hi;
     }
     tr.mark("enqueue");
+    const char* why = values_ok();                 // overlaps with the GPU work enqueued above
+    tr.mark("finite");
     FQ_CUDA(cudaStreamSynchronize(ctx->stream2));
     FQ_CUDA(cudaStreamSynchronize(st));
     tr.mark("wait");
+    if (why) return fail(ctx, FQ_E_ARG, why);      // outputs were written but are not to be trusted
     return 0;
   }
   if (n_poly == 0) FQ_CUDA(cudaMemsetAsync(din + L.sigma, 0, sig_bytes, st));
