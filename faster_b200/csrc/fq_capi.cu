@@ -73,7 +73,7 @@ struct fq_ctx
   unsigned counters_pos = 0;
   int max_poly_faces_hint = 0;    // option "max_faces_per_polytope" (device-pointer API only)
 };
-static const int kCounterSlots = 16;
+static const int kCounterSlots = 64;
 
 namespace
 {

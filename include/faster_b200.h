@@ -40,7 +40,11 @@ typedef struct fq_ctx fq_ctx;     /* opaque: device, stream, plan tables, scratc
 
 int fq_abi_version(void);
 
-/* Creates a solver context on CUDA device `device`.  Fails with FQ_E_NOGPU when no usable GPU exists:
+/* Threading: a context is used from one thread at a time, like a SolverGurobi instance in the reference (one replan
+ * callback); different contexts are independent.  With fq_solve_multi_dev at most 64 launches of one
+ * context may be in flight on DIFFERENT streams at once (launches on one stream are ordered and unlimited).
+ *
+ * Creates a solver context on CUDA device `device`.  Fails with FQ_E_NOGPU when no usable GPU exists:
  * there is no CPU fallback.  Replaces `new GRBEnv()` / GRBModel construction (solverGurobi.hpp:154-155). */
 int fq_create(fq_ctx** out, int device);
 void fq_destroy(fq_ctx* ctx);
