@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("FQ_LIB") or os.path.join(_HERE, "lib", "libfaster_b20
 _lib = None
 
 EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_set_option", "fq_solve_batch", "fq_solve_multi",
-           "fq_solve_multi_dev", "fq_gen_new_traj", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
+           "fq_solve_multi_dev", "fq_gen_new_traj", "fq_gen_new_traj_sampled", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
            "fq_monotone_sigmas", "fq_plan_tables", "fq_ellipsoid_decomp"]
 
 
@@ -50,6 +50,9 @@ def lib():
                                         [C.c_int, C.c_int] + [C.c_void_p] * 7
         L.fq_gen_new_traj.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + \
                                      [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.fq_gen_new_traj_sampled.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + \
+                                             [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_double, C.c_int] + [C.c_void_p] * 6
         _lib = L
     return _lib
 
@@ -195,6 +198,23 @@ class Solver:
                                                d_lim, d_poly_ofs, d_face_ofs, d_Ab, d_cand_ofs, int(max_cand),
                                                int(max_faces), d_dt, d_sigma, d_feas, d_cost, d_coeffs or None,
                                                d_iters or None, stream or None))
+
+    def gen_new_traj_sampled(self, N, x0, xf, lim, polys, dts, sigmas, DC, force_final=True, max_samples=8192):
+        """gen_new_traj + fillX on the device -> dict(solved, dt_index, sigma_index, cost, coeffs, X[n,12])."""
+        P, ofs, Ab = pack_polys(polys)
+        dts = _f64(dts)
+        sig = np.ascontiguousarray(np.asarray(sigmas, np.uint8).reshape(-1, N)) if P > 0 else np.zeros((1, N), np.uint8)
+        x0, xf, lim = _f64(x0, 9), _f64(xf, 9), _f64(lim, 3)
+        di, si, cost, ns = C.c_int(-1), C.c_int(-1), C.c_double(np.inf), C.c_int(0)
+        co = np.zeros((N, 12))
+        X = np.zeros((max_samples, 12))
+        rc = self._check(self._L.fq_gen_new_traj_sampled(self._h, int(N), int(bool(force_final)), x0.ctypes.data,
+                                                         xf.ctypes.data, lim.ctypes.data, P, ofs.ctypes.data,
+                                                         Ab.ctypes.data, dts.size, dts.ctypes.data, sig.shape[0],
+                                                         sig.ctypes.data, float(DC), int(max_samples), C.addressof(di),
+                                                         C.addressof(si), C.addressof(cost), co.ctypes.data, X.ctypes.data,
+                                                         C.addressof(ns)))
+        return dict(solved=bool(rc), dt_index=di.value, sigma_index=si.value, cost=cost.value, coeffs=co, X=X[:ns.value])
 
     def gen_new_traj(self, N, x0, xf, lim, polys, dts, sigmas, force_final=True):
         """-> dict(solved, dt_index, sigma_index, cost, coeffs[N,12])."""

@@ -468,10 +468,12 @@ extern "C" int fq_solve_batch(fq_ctx* ctx, int N, int force_final, const double*
                         sigma, feasible, cost, coeffs, iters);
 }
 
-extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf,
-                               const double* lim, int P, const int* face_ofs, const double* Ab, int n_dt,
-                               const double* dts, int n_sigma, const uint8_t* sigmas, int* dt_index,
-                               int* sigma_index, double* cost, double* coeffs)
+namespace
+{
+int gen_new_traj_impl(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf, const double* lim, int P,
+                      const int* face_ofs, const double* Ab, int n_dt, const double* dts, int n_sigma,
+                      const uint8_t* sigmas, int* dt_index, int* sigma_index, double* cost, double* coeffs, double DC,
+                      int max_samples, double* samples, int* n_samples)
 {
   if (!ctx) return FQ_E_ARG;
   Trace tr;
@@ -505,19 +507,23 @@ extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double
   const size_t opo = o;   o += sizeof(int) * 2;
   const size_t ofo = o;   o += sizeof(int) * (size_t)(P + 1);
   const size_t oco = o;   o += sizeof(int) * 2;
-  const size_t osig = o;  o += (size_t)n_cand * N;
+  const size_t osig = o;  o = align16(o + (size_t)n_cand * N);
+  const size_t odts = o;  o += sizeof(double) * (size_t)n_dt;      // the n_dt distinct time allocations (for fillX)
   const size_t in_bytes = align16(o);
   o = 0;
   const size_t ocost = o;   o += sizeof(double) * (size_t)n_cand;
   const size_t ocoef = o;   o += sizeof(double) * 12 * (size_t)N * n_cand;
   const size_t owin = o;    o += sizeof(double) * (1 + 12 * (size_t)N);     // winner: cost + coeffs
   const size_t oidx = o;    o += sizeof(int) * 2;
+  const size_t onsamp = o;  o += sizeof(int) * 2;
+  const size_t osamp = o;   o += samples ? sizeof(double) * 12 * (size_t)max_samples : 0;
   const size_t ofeas = o;   o += (size_t)n_cand;
   const size_t out_bytes = align16(o);
   FQ_CUDA(ctx->d_in.reserve(in_bytes));
   FQ_CUDA(ctx->d_out.reserve(out_bytes));
   FQ_CUDA(ctx->h_in.reserve(in_bytes));
-  FQ_CUDA(ctx->h_out.reserve(sizeof(double) * (1 + 12 * (size_t)N) + 2 * sizeof(int)));
+  FQ_CUDA(ctx->h_out.reserve(sizeof(double) * (1 + 12 * (size_t)N) + 4 * sizeof(int) +
+                             (samples ? sizeof(double) * 12 * (size_t)max_samples : 0)));
   char* hi = (char*)ctx->h_in.p;
   if (n_face) std::memcpy(hi + oAb, Ab, sizeof(double) * 4 * (size_t)n_face);
   std::memcpy(hi + ox0, x0, sizeof(double) * 9);
@@ -533,6 +539,7 @@ extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double
         if (P > 0) std::memcpy(hs + ((size_t)d * n_sigma + s) * N, sigmas + (size_t)s * N, N);
         else std::memset(hs + ((size_t)d * n_sigma + s) * N, 0, N);
       }
+    std::memcpy(hi + odts, dts, sizeof(double) * (size_t)n_dt);
     int* po = (int*)(hi + opo); po[0] = 0; po[1] = P;
     int* fo = (int*)(hi + ofo); fo[0] = 0; for (int p = 0; p < P; p++) fo[p + 1] = face_ofs[p + 1];
     int* co = (int*)(hi + oco); co[0] = 0; co[1] = n_cand;
@@ -556,7 +563,17 @@ extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double
   FQ_CUDA(fq_launch_select(sa, st));
   char* ho = (char*)ctx->h_out.p;
   const size_t win_bytes = sizeof(double) * (1 + 12 * (size_t)N);
-  FQ_CUDA(cudaMemcpyAsync(ho, dout + owin, win_bytes + 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  size_t tail_bytes = 2 * sizeof(int);
+  if (samples)
+  { // fillX on the device, chained on the same stream; samples travel back with the winner record
+    FqFillArgs fa;
+    fa.N = N; fa.n_dt = n_dt; fa.max_samples = max_samples; fa.DC = DC;
+    fa.dts = (const double*)(din + odts); fa.win_idx = (const int*)(dout + oidx);
+    fa.coeffs = (const double*)(dout + owin) + 1; fa.out = (double*)(dout + osamp); fa.n_samples = (int*)(dout + onsamp);
+    FQ_CUDA(fq_launch_fill(fa, st));
+    tail_bytes = 4 * sizeof(int) + sizeof(double) * 12 * (size_t)max_samples;
+  }
+  FQ_CUDA(cudaMemcpyAsync(ho, dout + owin, win_bytes + tail_bytes, cudaMemcpyDeviceToHost, st));
   tr.mark("enqueue");
   FQ_CUDA(cudaStreamSynchronize(st));
   tr.mark("wait");
@@ -565,8 +582,37 @@ extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double
   const double* win = (const double*)ho;
   if (dt_index) *dt_index = idx[0];
   if (sigma_index) *sigma_index = idx[1];
+  if (n_samples) *n_samples = 0;
   if (idx[0] < 0) { if (cost) *cost = INFINITY; return 0; }
   if (cost) *cost = win[0];
   if (coeffs) std::memcpy(coeffs, win + 1, sizeof(double) * 12 * (size_t)N);
+  if (samples)
+  {
+    const int ns = idx[2];
+    if (n_samples) *n_samples = ns;
+    std::memcpy(samples, ho + win_bytes + 4 * sizeof(int), sizeof(double) * 12 * (size_t)ns);
+  }
   return 1;
+}
+}  // namespace
+
+extern "C" int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf,
+                               const double* lim, int P, const int* face_ofs, const double* Ab, int n_dt,
+                               const double* dts, int n_sigma, const uint8_t* sigmas, int* dt_index,
+                               int* sigma_index, double* cost, double* coeffs)
+{
+  return gen_new_traj_impl(ctx, N, force_final, x0, xf, lim, P, face_ofs, Ab, n_dt, dts, n_sigma, sigmas, dt_index,
+                           sigma_index, cost, coeffs, 0.0, 0, nullptr, nullptr);
+}
+
+extern "C" int fq_gen_new_traj_sampled(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf,
+                                       const double* lim, int P, const int* face_ofs, const double* Ab, int n_dt,
+                                       const double* dts, int n_sigma, const uint8_t* sigmas, double DC,
+                                       int max_samples, int* dt_index, int* sigma_index, double* cost,
+                                       double* coeffs, double* samples, int* n_samples)
+{
+  if (!ctx) return FQ_E_ARG;
+  if (!samples || max_samples < 2 || !(DC > 0)) return fail(ctx, FQ_E_ARG, "samples buffer, max_samples >= 2 and DC > 0 required");
+  return gen_new_traj_impl(ctx, N, force_final, x0, xf, lim, P, face_ofs, Ab, n_dt, dts, n_sigma, sigmas, dt_index,
+                           sigma_index, cost, coeffs, DC, max_samples, samples, n_samples);
 }

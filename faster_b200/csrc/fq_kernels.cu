@@ -461,6 +461,53 @@ __global__ void __launch_bounds__(256) fq_select_kernel(const FqSelectArgs a)
   if (a.coeffs && a.out_coeffs)
     for (int i = threadIdx.x; i < 12 * a.N; i += blockDim.x) a.out_coeffs[i] = a.coeffs[(size_t)win * 12 * a.N + i];
 }
+
+// fillX on the device (reference solverGurobi.cpp:122-168, resetX :382-388).  The reference accumulates the sample time
+// (`t = t + DC`) and advances the interval index by at most one per sample; both are reproduced exactly: thread i
+// replays the i+1 additions, and -- because findDT keeps dt >= 2 DC (:494-497) so that a sample crosses at most one knot --
+// the lagging interval index equals the number of knots m*dt (m >= 1) strictly below t, capped at N-1.  A sample that
+// would need more than one advance (dt < DC, impossible through findDT) is detected and handled by a sequential replay.
+__global__ void __launch_bounds__(256) fq_fill_kernel(const FqFillArgs a)
+{
+  const int w = a.win_idx[0];
+  if (w < 0) { if (threadIdx.x == 0 && blockIdx.x == 0) a.n_samples[0] = 0; return; }
+  const double dt = a.dts[w], DC = a.DC;
+  int n = (int)((int)(a.N)*dt / DC);
+  n = n < 2 ? 2 : n;
+  if (n > a.max_samples) n = a.max_samples;
+  if (threadIdx.x == 0 && blockIdx.x == 0) a.n_samples[0] = n;
+  const bool lagging_ok = dt >= DC;            // at most one knot per sample
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    double t = 0;
+    int interval = 0;
+    if (lagging_ok)
+    {
+      for (int k = 0; k <= i; k++) t = t + DC;
+      while (interval < a.N - 1 && t > dt * (interval + 1)) interval++;
+    }
+    else
+    {
+      for (int k = 0; k <= i; k++)
+      {
+        t = t + DC;
+        if (t > dt * (interval + 1)) interval = min(interval + 1, a.N - 1);
+      }
+    }
+    const double tau = t - interval * dt;
+    const double* x = a.coeffs + 12 * interval;
+    double* o = a.out + (size_t)12 * i;
+    const bool last = i == n - 1;              // :165-167: the last sample's vel/accel/jerk are zeroed
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++)
+    {
+      o[ax] = x[ax] * tau * tau * tau + x[3 + ax] * tau * tau + x[6 + ax] * tau + x[9 + ax];
+      o[3 + ax] = last ? 0.0 : 3 * x[ax] * tau * tau + 2 * x[3 + ax] * tau + x[6 + ax];
+      o[6 + ax] = last ? 0.0 : 6 * x[ax] * tau + 2 * x[3 + ax];
+      o[9 + ax] = last ? 0.0 : 6 * x[ax];
+    }
+  }
+}
 }  // namespace
 
 #include "fq_kernels_t.cuh"
@@ -506,6 +553,15 @@ cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaSt
   const long long blocks = (long long)chunks * a.n_prob;
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
   fq_solve_kernel<<<(unsigned)blocks, W * 32, smem, stream>>>(a, chunks);
+  return cudaGetLastError();
+}
+
+cudaError_t fq_launch_fill(const FqFillArgs& a, cudaStream_t stream)
+{
+  int blocks = (a.max_samples + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 64) blocks = 64;
+  fq_fill_kernel<<<blocks, 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -50,6 +50,19 @@ struct FqSelectArgs
   double* out_coeffs;    // N x 12
 };
 
+// device-side fillX (solverGurobi.cpp:122-168) of the winner selected by fq_select_kernel
+struct FqFillArgs
+{
+  int N, n_dt, max_samples;
+  double DC;
+  const double* dts;        // n_dt, device
+  const int* win_idx;       // [0] winning dt index (-1: nothing to sample)
+  const double* coeffs;     // N x 12 of the winner
+  double* out;              // max_samples x 12
+  int* n_samples;           // [0] number of samples written
+};
+cudaError_t fq_launch_fill(const FqFillArgs& a, cudaStream_t stream);
+
 size_t fq_solve_smem_bytes(const FqKernelArgs& a);
 // picks the size-specialised kernel when one exists (4 <= N <= 16, faces <= 2047), else the generic one;
 // force_generic selects the generic kernel regardless (differential testing)

@@ -97,6 +97,16 @@ int fq_gen_new_traj(fq_ctx* ctx, int N, int force_final, const double* x0, const
                     int P, const int* face_ofs, const double* Ab, int n_dt, const double* dts, int n_sigma,
                     const uint8_t* sigmas, int* dt_index, int* sigma_index, double* cost, double* coeffs);
 
+/* fq_gen_new_traj followed by fillX ON THE DEVICE (solverGurobi.cpp:122-168, resetX :382-388), chained on the same
+ * stream: solve launch -> selection -> sampling kernel -> one D2H.  `samples` receives min(n, max_samples) rows of 12
+ * doubles (pos vel accel jerk at t = (i+1) DC, last row's vel/accel/jerk zeroed), n = max(2, (int)(N dt/DC)) for the
+ * winning dt; *n_samples is the count.  Same return convention as fq_gen_new_traj.  Provided for completeness and
+ * measured in DESIGN.md: sampling on the host from the 96 N bytes of coefficients (fq_fill_x) is the faster route. */
+int fq_gen_new_traj_sampled(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf, const double* lim,
+                            int P, const int* face_ofs, const double* Ab, int n_dt, const double* dts, int n_sigma,
+                            const uint8_t* sigmas, double DC, int max_samples, int* dt_index, int* sigma_index,
+                            double* cost, double* coeffs, double* samples, int* n_samples);
+
 /* ---- host-side helpers (no GPU needed) ------------------------------------------------------------- */
 
 /* getDTInitial (solverGurobi.cpp:659-759), including its float temporaries and MinPositiveElement

@@ -457,3 +457,29 @@ def test_cuda_reproduces_committed_goldens(solver, demo_corridor):
     dti = capi.dt_initial(fx["x0"], fx["xf"], fx["lim"], fx["N"])
     g = solver.gen_new_traj(fx["N"], fx["x0"], fx["xf"], fx["lim"], fx["polys"], np.arange(1.0, 11.0) * max(dti, 0.02), sig, True)
     assert g["solved"] == e["solved"] and g["dt_index"] + 1 == e["trials"] and abs(g["cost"] - e["cost"]) <= REL * e["cost"]
+
+
+def test_device_side_fill_x_matches_host(solver, oracle, demo_corridor):
+    """fq_gen_new_traj_sampled (fillX chained on the device) == fq_gen_new_traj + host fq_fill_x == oracle fillX."""
+    fx = demo_corridor
+    cases = [(fx["N"], fx["x0"], fx["xf"], fx["lim"], fx["polys"], True)]
+    for seed in range(3):
+        pb = cr.make_corridor(1300 + seed, 3, 6, force_final=bool(seed % 2))
+        cases.append((6, pb["x0"], pb["xf"], pb["lim"], pb["polys"], bool(seed % 2)))
+    DC = 0.01
+    n = 0
+    for N, x0, xf, lim, polys, ff in cases:
+        sig = cr.monotone_sigmas(N, len(polys))
+        dts = np.arange(1.0, 11.0) * max(capi.dt_initial(x0, xf, lim, N), 2 * DC)
+        a = solver.gen_new_traj(N, x0, xf, lim, polys, dts, sig, ff)
+        b = solver.gen_new_traj_sampled(N, x0, xf, lim, polys, dts, sig, DC, ff)
+        assert a["solved"] == b["solved"] and a["dt_index"] == b["dt_index"] and a["cost"] == b["cost"]
+        if a["solved"]:
+            dt = dts[a["dt_index"]]
+            Xh = capi.fill_x(N, a["coeffs"], dt, DC)
+            Xo = oracle.fill_x(N, a["coeffs"], dt, DC)
+            assert b["X"].shape == Xh.shape == Xo.shape
+            assert np.allclose(b["X"], Xh, rtol=1e-12, atol=1e-12) and np.allclose(b["X"], Xo, rtol=1e-12, atol=1e-12)
+            assert np.all(b["X"][-1, 3:] == 0)
+            n += 1
+    assert n >= 2
