@@ -1,17 +1,22 @@
-// Size-specialised solver kernel (compile-time N and whole/safe mode).  Same algorithm and same numerics policy as
-// the generic kernel in fq_kernels.cu (dual active-set on the normalised, equality-eliminated QP of fq_plan.h);
-// what changes is where things live and how the warp's lanes are used:
-//   * sizes are template constants: no integer division, bounded loops unroll, vectors live in registers;
+// Size-specialised solver kernel (compile-time N and whole/safe mode) -- the product path.  Same algorithm as the
+// generic kernel in fq_kernels.cu (dual active-set on the normalised, equality-eliminated QP of fq_plan.h) and the same
+// answers (the two are differential-tested on the GPU); what changes is where things live and how the lanes are used:
+//   * sizes are template constants: no integer division, bounded loops unroll, small vectors live in registers;
 //   * every lane OWNS fixed rows of Y (row y = lane + 32 r, all three axes): the plan's constant part Yeq stays in
 //     registers, Y = Yeq + TZ w costs one broadcast read of w per column, and the |v|,|a|,|j| box rows
-//     (solverGurobi.cpp:390-407) are checked by the owning lane while the value is still in a register;
+//     (solverGurobi.cpp:390-407) are ranked by the owning lane while the value is still in a register;
 //   * corridor rows (solverGurobi.cpp:249-287) are scanned through a per-candidate item list (segment, face), 32 rows
-//     per pass, one fmax tree per item; the control point that is shared with the previous segment is skipped when
-//     both segments use the same polytope;
+//     per pass; the control point shared with the previous segment is skipped when both segments use the same polytope;
+//   * the entering row is the one farthest beyond its hyperplane in w-space: rank = (violation - tol) / |TZ[y]|, compared
+//     through the hi word of that double as a signed int (positive <=> violated), so the warp arg-max is one redux.sync
+//     plus a ballot.  This "normalised pivoting" halves the iteration count relative to "largest violation";
 //   * duals, the triangular solve and the ratio test are register/shuffle based (element k of an NW-vector lives in
-//     lane k%32, slot k/32);  reciprocals and square roots use the MUFU seed + Newton steps instead of IEEE division;
-//   * a CTA owns a chunk of candidates of ONE problem (polytope rows staged once); its warps pull candidates from a
-//     shared counter so a slow candidate does not idle the other warps.
+//     lane k%32, slot k/32); reciprocals and square roots use the MUFU seed + Newton steps instead of IEEE division;
+//   * persistent CTAs: per-problem claim counters in global memory; a CTA adopts a problem that still has unclaimed
+//     candidates, stages its polytope rows once ([Ax Ay Az b+tol], checked for non-finite values), and its warps claim
+//     candidates one at a time, so nobody idles behind a slow candidate and block barriers happen only when a CTA
+//     changes problem;
+//   * non-finite or non-positive inputs make a candidate "not solved" up front (NaN rank keys would look satisfied).
 #pragma once
 
 namespace fqt
