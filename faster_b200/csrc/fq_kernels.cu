@@ -532,10 +532,12 @@ cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaSt
   if (!force_generic && fq_has_specialised(a.N, a.force_final, a.max_faces))
   {
     const long long total_hint = (long long)max_cand_per_prob * a.n_prob;
+    cudaError_t e = cudaErrorInvalidConfiguration;
 #define FQ_CASE(NN)                                                                                        \
   case NN:                                                                                                 \
-    return a.force_final ? fqt::launch_t<NN, true>(a, total_hint, stream, counters, sm_count)                        \
-                         : fqt::launch_t<NN, false>(a, total_hint, stream, counters, sm_count);
+    e = a.force_final ? fqt::launch_t<NN, true>(a, total_hint, stream, counters, sm_count)                            \
+                      : fqt::launch_t<NN, false>(a, total_hint, stream, counters, sm_count);                          \
+    break;
     switch (a.N)
     {
       FQ_CASE(4) FQ_CASE(5) FQ_CASE(6) FQ_CASE(7) FQ_CASE(8) FQ_CASE(9) FQ_CASE(10) FQ_CASE(11) FQ_CASE(12)
@@ -543,6 +545,9 @@ cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaSt
       default: break;
     }
 #undef FQ_CASE
+    // cudaErrorInvalidConfiguration: the problem (very many faces per polytope) does not fit the specialised kernel's
+    // shared-memory layout -> the size-generic kernel below takes it
+    if (e != cudaErrorInvalidConfiguration) return e;
   }
   const size_t smem = fq_solve_smem_bytes(a);
   {  // per-device attribute; cheap enough to set on every launch (contexts on several GPUs share this code)

@@ -698,7 +698,7 @@ template <int N_, bool WHOLE_>
 cudaError_t launch_t(const FqKernelArgs& a, long long total_cand_hint, cudaStream_t stream, int* counters, int sm_count)
 {
   const size_t smem = smem_bytes_t<N_, WHOLE_>(a.max_faces, a.item_cap);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;   // caller falls back to the size-generic kernel
   auto kern = fq_solve_kernel_t<N_, WHOLE_>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -483,3 +483,23 @@ def test_device_side_fill_x_matches_host(solver, oracle, demo_corridor):
             assert np.all(b["X"][-1, 3:] == 0)
             n += 1
     assert n >= 2
+
+
+def test_huge_polytopes_fall_back_to_generic_kernel(solver, oracle):
+    """Polytopes with hundreds of faces exceed the specialised kernel's per-warp row list in shared memory: the launch
+    falls back to the size-generic kernel and still agrees with the oracle."""
+    rng = np.random.default_rng(77)
+    pb = cr.make_corridor(61, 3, 10)
+    fat = []
+    for (A, b), (v0, v1) in zip(pb["polys"], zip(pb["verts"][:-1], pb["verts"][1:])):
+        mid = 0.5 * (v0 + v1)
+        n = rng.normal(size=(700 - len(b), 3))
+        n /= np.linalg.norm(n, axis=1, keepdims=True)
+        fat.append((np.vstack([A, n]), np.concatenate([b, n @ mid + rng.uniform(2.5, 4.0, len(n))])))
+    sig = cr.monotone_sigmas(10, 3)[::3]
+    dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], 10)
+    dts = np.repeat(np.array([1.5, 2.5, 4.0]) * dti, len(sig))
+    sigs = np.tile(sig, (3, 1))
+    fg, cg, cog, _ = solver.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], fat, dts, sigs, True, True)
+    fo, co_, coo = oracle.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], fat, dts, sigs, True, True, threads=8)
+    _compare(fg, cg, cog, fo, co_, coo, "700-face polytopes")
