@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("FQ_LIB") or os.path.join(_HERE, "lib", "libfaster_b20
 _lib = None
 
 EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_set_option", "fq_solve_batch", "fq_solve_multi",
-           "fq_solve_multi_dev", "fq_gen_new_traj", "fq_gen_new_traj_sampled", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
+           "fq_solve_multi_dev", "fq_gen_new_traj", "fq_gen_new_traj_sampled", "fq_gen_new_traj_exact", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
            "fq_monotone_sigmas", "fq_plan_tables", "fq_ellipsoid_decomp"]
 
 
@@ -215,6 +215,23 @@ class Solver:
                                                          C.addressof(si), C.addressof(cost), co.ctypes.data, X.ctypes.data,
                                                          C.addressof(ns)))
         return dict(solved=bool(rc), dt_index=di.value, sigma_index=si.value, cost=cost.value, coeffs=co, X=X[:ns.value])
+
+    def gen_new_traj_exact(self, N, x0, xf, lim, polys, dts, force_final=True):
+        """Exact MIQP sweep (branch-and-bound over all assignments) -> dict(solved, dt_index, sigma, cost, coeffs, nodes, exact)."""
+        P, ofs, Ab = pack_polys(polys)
+        dts = _f64(dts)
+        x0, xf, lim = _f64(x0, 9), _f64(xf, 9), _f64(lim, 3)
+        di, cost, nodes, exact = C.c_int(-1), C.c_double(np.inf), C.c_long(0), C.c_int(0)
+        sig = np.zeros(N, np.uint8)
+        co = np.zeros((N, 12))
+        self._L.fq_gen_new_traj_exact.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_void_p,
+                                                   C.c_int] + [C.c_void_p] * 7
+        rc = self._check(self._L.fq_gen_new_traj_exact(self._h, int(N), int(bool(force_final)), x0.ctypes.data, xf.ctypes.data,
+                                                       lim.ctypes.data, P, ofs.ctypes.data, Ab.ctypes.data, dts.size,
+                                                       dts.ctypes.data, C.addressof(di), sig.ctypes.data, C.addressof(cost),
+                                                       co.ctypes.data, C.addressof(nodes), C.addressof(exact)))
+        return dict(solved=bool(rc), dt_index=di.value, sigma=sig, cost=cost.value, coeffs=co, nodes=nodes.value,
+                    exact=bool(exact.value))
 
     def gen_new_traj(self, N, x0, xf, lim, polys, dts, sigmas, force_final=True):
         """-> dict(solved, dt_index, sigma_index, cost, coeffs[N,12])."""

@@ -63,7 +63,7 @@ struct fq_ctx
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev_head = nullptr;
   std::map<int, PlanDev> plans;   // key N*2+force_final
-  Arena d_in, d_out;
+  Arena d_in, d_out, d_bnb;
   PinnedArena h_in, h_out;
   std::string err;
   bool force_generic = false;
@@ -161,7 +161,7 @@ extern "C" void fq_destroy(fq_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (auto& kv : ctx->plans) { cudaFree(kv.second.TZ); cudaFree(kv.second.T0); cudaFree(kv.second.FT); }
-  ctx->d_in.release(); ctx->d_out.release(); ctx->h_in.release(); ctx->h_out.release();
+  ctx->d_in.release(); ctx->d_out.release(); ctx->d_bnb.release(); ctx->h_in.release(); ctx->h_out.release();
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->ev_head) cudaEventDestroy(ctx->ev_head);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -615,4 +615,210 @@ extern "C" int fq_gen_new_traj_sampled(fq_ctx* ctx, int N, int force_final, cons
   if (!samples || max_samples < 2 || !(DC > 0)) return fail(ctx, FQ_E_ARG, "samples buffer, max_samples >= 2 and DC > 0 required");
   return gen_new_traj_impl(ctx, N, force_final, x0, xf, lim, P, face_ofs, Ab, n_dt, dts, n_sigma, sigmas, dt_index,
                            sigma_index, cost, coeffs, DC, max_samples, samples, n_samples);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Exact MIQP sweep: genNewTraj with the minimum over ALL P^N assignments (what Gurobi's branch-and-bound returns), by
+// branch-and-bound on the GPU (fq_bnb.cuh).  Only the time allocations up to the first one that is feasible for a
+// non-decreasing assignment can win (first feasible factor wins, solverGurobi.cpp:445-446), so only those are searched.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf,
+                                     const double* lim, int P, const int* face_ofs, const double* Ab, int n_dt,
+                                     const double* dts, int* dt_index, uint8_t* sigma_out, double* cost, double* coeffs,
+                                     long* nodes_out, int* exact_out)
+{
+  if (!ctx) return FQ_E_ARG;
+  if (!x0 || !xf || !lim || !dts || n_dt <= 0) return fail(ctx, FQ_E_ARG, "NULL argument or n_dt <= 0");
+  if (P < 0 || P > FQ_MAX_POLY) return fail(ctx, FQ_E_ARG, "bad P");
+  if (nodes_out) *nodes_out = 0;
+  if (exact_out) *exact_out = 1;
+  if (sigma_out) std::memset(sigma_out, 0, (size_t)N);
+  if (P == 0)
+    return gen_new_traj_impl(ctx, N, force_final, x0, xf, lim, 0, face_ofs, Ab, n_dt, dts, 1, nullptr, dt_index, nullptr, cost,
+                             coeffs, 0.0, 0, nullptr, nullptr);
+  if (!face_ofs || !Ab) return fail(ctx, FQ_E_ARG, "polytopes missing");
+  const int n_face = face_ofs[P];
+  int max_pf = 0;
+  for (int p = 0; p < P; p++) max_pf = std::max(max_pf, face_ofs[p + 1] - face_ofs[p]);
+  const size_t nb = fq_bnb_node_bytes(N, force_final);
+  // ---- 1. non-decreasing assignments for every time allocation (the ordinary batch solve)
+  const long n_mono = fq_monotone_sigmas(N, P, nullptr, 0);
+  if (n_mono <= 0 || n_mono > (1L << 20)) return fail(ctx, FQ_E_ARG, "assignment list too long");
+  std::vector<uint8_t> mono((size_t)n_mono * N);
+  fq_monotone_sigmas(N, P, mono.data(), n_mono);
+  const size_t n_cand = (size_t)n_dt * n_mono;
+  std::vector<double> gdt(n_cand), gcost(n_cand);
+  std::vector<uint8_t> gsig(n_cand * N), gfeas(n_cand);
+  for (int d = 0; d < n_dt; d++)
+    for (long k = 0; k < n_mono; k++)
+    {
+      gdt[(size_t)d * n_mono + k] = dts[d];
+      std::memcpy(&gsig[((size_t)d * n_mono + k) * N], &mono[(size_t)k * N], N);
+    }
+  int rc = fq_solve_batch(ctx, N, force_final, x0, xf, lim, P, face_ofs, Ab, (int)n_cand, gdt.data(), gsig.data(), gfeas.data(),
+                          gcost.data(), nullptr, nullptr);
+  if (rc) return rc;
+  std::vector<double> best(n_dt, INFINITY);
+  std::vector<long> best_k(n_dt, -1);
+  int fstar = -1;
+  for (int d = 0; d < n_dt; d++)
+  {
+    for (long k = 0; k < n_mono; k++)
+      if (gfeas[(size_t)d * n_mono + k] && gcost[(size_t)d * n_mono + k] < best[d]) { best[d] = gcost[(size_t)d * n_mono + k]; best_k[d] = k; }
+    if (fstar < 0 && best_k[d] >= 0) fstar = d;
+  }
+  const int n_search = fstar >= 0 ? fstar + 1 : n_dt;       // later time allocations cannot win
+  bool exact = nb != 0 && n_face <= 2047;
+  std::vector<uint8_t> win_sigma(N, 0);
+  int win_dt = -1;
+  if (exact)
+  {
+    // ---- 2. device buffers
+    const int cap = 65536, leaf_cap = 4096;
+    size_t o = 0;
+    const size_t oAb = o;    o = align16(o + sizeof(double) * 4 * (size_t)n_face);
+    const size_t ox0 = o;    o += sizeof(double) * 9;
+    const size_t oxf = o;    o += sizeof(double) * 9;
+    const size_t olim = o;   o += sizeof(double) * 3;
+    const size_t odts = o;   o += sizeof(double) * (size_t)n_dt;
+    const size_t oinc = o;   o += sizeof(unsigned long long) * (size_t)n_dt;
+    const size_t opo = o;    o += sizeof(int) * 2;
+    const size_t ofo = o;    o += sizeof(int) * (size_t)(P + 1);
+    const size_t oroot = o;  o += sizeof(int) * (size_t)n_dt;
+    const size_t ocnt = o;   o = align16(o + sizeof(int) * 8);   // [0] n_children [1] n_leaves [2..3] flags
+    const size_t head = o;
+    const size_t oleaf = o;  o = align16(o + 32 * (size_t)leaf_cap);
+    const size_t opoolA = o; o = align16(o + nb * (size_t)cap);
+    const size_t opoolB = o; o = align16(o + nb * (size_t)cap);
+    FQ_CUDA(cudaSetDevice(ctx->device));
+    FQ_CUDA(ctx->d_bnb.reserve(o));
+    FQ_CUDA(ctx->h_in.reserve(head));
+    char* hi = (char*)ctx->h_in.p;
+    char* db = (char*)ctx->d_bnb.p;
+    std::memset(hi, 0, head);
+    std::memcpy(hi + oAb, Ab, sizeof(double) * 4 * (size_t)n_face);
+    std::memcpy(hi + ox0, x0, sizeof(double) * 9);
+    std::memcpy(hi + oxf, xf, sizeof(double) * 9);
+    std::memcpy(hi + olim, lim, sizeof(double) * 3);
+    std::memcpy(hi + odts, dts, sizeof(double) * (size_t)n_dt);
+    // presolve on the constant control points: segment 0 starts with cp0, cp1, cp2 fixed by (x0, dt) and, with the final
+    // position pinned, the last control point is xf -- a time allocation for which no polytope holds them is infeasible
+    // for EVERY assignment and needs no tree (otherwise such corridors make the tree explore all prefixes)
+    auto inside_any = [&](const double* pt) {
+      for (int p = 0; p < P; p++)
+      {
+        bool in = true;
+        for (int f = face_ofs[p]; f < face_ofs[p + 1] && in; f++)
+          in = Ab[4 * f] * pt[0] + Ab[4 * f + 1] * pt[1] + Ab[4 * f + 2] * pt[2] - Ab[4 * f + 3] <= FQ_ROW_TOL;
+        if (in) return true;
+      }
+      return false;
+    };
+    int n_roots = 0;
+    for (int d = 0; d < n_dt; d++)
+    {
+      unsigned long long bits;
+      const double c = best[d];
+      std::memcpy(&bits, &c, 8);
+      ((unsigned long long*)(hi + oinc))[d] = bits;              // +inf orders above every finite cost
+      if (d >= n_search) continue;
+      bool possible = true;
+      if (force_final) possible = inside_any(xf);
+      if (possible)
+      { // all three constant points of segment 0 must share one polytope
+        possible = false;
+        const double t = dts[d];
+        for (int p = 0; p < P && !possible; p++)
+        {
+          bool in = true;
+          for (int kk = 0; kk < 3 && in; kk++)
+          {
+            double pt[3];
+            for (int ax = 0; ax < 3; ax++)
+              pt[ax] = x0[ax] + (kk >= 1 ? x0[3 + ax] * t * (kk == 1 ? 1.0 / 3.0 : 2.0 / 3.0) : 0.0) + (kk == 2 ? x0[6 + ax] * t * t / 6.0 : 0.0);
+            for (int f = face_ofs[p]; f < face_ofs[p + 1] && in; f++)
+              in = Ab[4 * f] * pt[0] + Ab[4 * f + 1] * pt[1] + Ab[4 * f + 2] * pt[2] - Ab[4 * f + 3] <= FQ_ROW_TOL;
+          }
+          possible = in;
+        }
+      }
+      if (possible) ((int*)(hi + oroot))[n_roots++] = d;
+    }
+    ((int*)(hi + opo))[0] = 0; ((int*)(hi + opo))[1] = P;
+    for (int p = 0; p <= P; p++) ((int*)(hi + ofo))[p] = face_ofs[p];
+    cudaStream_t st = ctx->stream;
+    FQ_CUDA(cudaMemcpyAsync(db, hi, head, cudaMemcpyHostToDevice, st));
+    PlanDev* pd = nullptr;
+    rc = get_plan(ctx, N, force_final, &pd);
+    if (rc) return rc;
+    FqBnbLevel L;
+    fill_plan_args(*pd, &L.k);
+    L.k.n_prob = 1; L.k.x0 = (const double*)(db + ox0); L.k.xf = (const double*)(db + oxf); L.k.lim = (const double*)(db + olim);
+    L.k.poly_ofs = (const int*)(db + opo); L.k.face_ofs = (const int*)(db + ofo); L.k.Ab = (const double*)(db + oAb);
+    L.k.max_faces = n_face; L.k.item_cap = N * max_pf; L.k.cand_ofs = nullptr; L.k.dt = nullptr; L.k.sigma = nullptr;
+    L.k.feasible = nullptr; L.k.cost = nullptr; L.k.coeffs = nullptr; L.k.iters = nullptr;
+    L.n_dt = n_dt; L.P = P; L.dts = (const double*)(db + odts); L.roots = (const int*)(db + oroot);
+    L.incumbent = (unsigned long long*)(db + oinc); L.leaves = db + oleaf; L.n_leaves = (int*)(db + ocnt) + 1;
+    L.leaf_cap = leaf_cap; L.flags = (int*)(db + ocnt) + 2; L.n_children = (int*)(db + ocnt); L.cap = cap;
+    int n_par = n_roots;
+    long nodes = 0;
+    unsigned char* pools[2] = { (unsigned char*)(db + opoolA), (unsigned char*)(db + opoolB) };
+    int cnt[4] = { 0, 0, 0, 0 };
+    for (int depth = 0; depth < N && n_par > 0; depth++)
+    {
+      L.depth = depth; L.n_parents = n_par;
+      L.parents = pools[depth & 1]; L.children = pools[(depth + 1) & 1];
+      FQ_CUDA(cudaMemsetAsync(L.n_children, 0, sizeof(int), st));
+      cudaError_t e = fq_launch_bnb_level(L, st);
+      if (e == cudaErrorInvalidConfiguration) { exact = false; break; }
+      FQ_CUDA(e);
+      FQ_CUDA(cudaMemcpyAsync(cnt, db + ocnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+      FQ_CUDA(cudaStreamSynchronize(st));
+      nodes += (long)n_par * P;
+      if (cnt[2]) { exact = false; break; }                      // pool overflow: the tree was cut
+      n_par = cnt[0];
+    }
+    if (nodes_out) *nodes_out = nodes;
+    if (exact)
+    {
+      const int n_leaves = std::min(cnt[1], leaf_cap);
+      struct Leaf { int dt_idx, pad; double cost; unsigned char sigma[16]; };
+      std::vector<Leaf> leaves((size_t)std::max(n_leaves, 1));
+      std::vector<unsigned long long> inc(n_dt);
+      if (n_leaves) FQ_CUDA(cudaMemcpyAsync(leaves.data(), db + oleaf, sizeof(Leaf) * (size_t)n_leaves, cudaMemcpyDeviceToHost, st));
+      FQ_CUDA(cudaMemcpyAsync(inc.data(), db + oinc, sizeof(unsigned long long) * (size_t)n_dt, cudaMemcpyDeviceToHost, st));
+      FQ_CUDA(cudaStreamSynchronize(st));
+      for (int d = 0; d < n_search && win_dt < 0; d++)
+      {
+        double c;
+        std::memcpy(&c, &inc[d], 8);
+        if (!(c < INFINITY)) continue;
+        win_dt = d;
+        bool from_leaf = false;
+        for (int i = 0; i < n_leaves; i++)                         // the last improving leaf of this dt holds the incumbent
+          if (leaves[i].dt_idx == d && leaves[i].cost == c) { std::memcpy(win_sigma.data(), leaves[i].sigma, N); from_leaf = true; }
+        if (!from_leaf) std::memcpy(win_sigma.data(), &mono[(size_t)best_k[d] * N], N);
+      }
+    }
+  }
+  if (!exact)
+  { // fall back to the non-decreasing optimum (reported through exact_out = 0)
+    if (exact_out) *exact_out = 0;
+    win_dt = fstar;
+    if (fstar >= 0) std::memcpy(win_sigma.data(), &mono[(size_t)best_k[fstar] * N], N);
+  }
+  if (dt_index) *dt_index = win_dt;
+  if (win_dt < 0) { if (cost) *cost = INFINITY; return 0; }
+  if (sigma_out) std::memcpy(sigma_out, win_sigma.data(), N);
+  // ---- 3. coefficients of the winner: one ordinary fixed-assignment solve
+  uint8_t f1 = 0;
+  double c1 = INFINITY;
+  std::vector<double> co((size_t)12 * N);
+  rc = fq_solve_batch(ctx, N, force_final, x0, xf, lim, P, face_ofs, Ab, 1, &dts[win_dt], win_sigma.data(), &f1, &c1, co.data(), nullptr);
+  if (rc) return rc;
+  if (!f1) return fail(ctx, FQ_E_CUDA, "internal: the winning assignment did not re-solve");
+  if (cost) *cost = c1;
+  if (coeffs) std::memcpy(coeffs, co.data(), sizeof(double) * 12 * (size_t)N);
+  return 1;
 }

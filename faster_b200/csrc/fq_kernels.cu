@@ -511,6 +511,7 @@ __global__ void __launch_bounds__(256) fq_fill_kernel(const FqFillArgs a)
 }  // namespace
 
 #include "fq_kernels_t.cuh"
+#include "fq_bnb.cuh"
 
 size_t fq_solve_smem_bytes(const FqKernelArgs& a)
 {
@@ -574,4 +575,33 @@ cudaError_t fq_launch_select(const FqSelectArgs& a, cudaStream_t stream)
 {
   fq_select_kernel<<<1, 256, 0, stream>>>(a);
   return cudaGetLastError();
+}
+
+size_t fq_bnb_node_bytes(int N, int force_final)
+{
+#define FQ_CASE(NN) case NN: return force_final ? fqb::node_bytes<fqt::Dims<NN, true>>() : fqb::node_bytes<fqt::Dims<NN, false>>();
+  switch (N)
+  {
+    FQ_CASE(4) FQ_CASE(5) FQ_CASE(6) FQ_CASE(7) FQ_CASE(8) FQ_CASE(9) FQ_CASE(10) FQ_CASE(11) FQ_CASE(12)
+    FQ_CASE(13) FQ_CASE(14) FQ_CASE(15) FQ_CASE(16)
+    default: return 0;
+  }
+#undef FQ_CASE
+}
+
+cudaError_t fq_launch_bnb_level(const FqBnbLevel& l, cudaStream_t stream)
+{
+  fqb::BnbArgs b;
+  b.k = l.k; b.n_dt = l.n_dt; b.P = l.P; b.dts = l.dts; b.depth = l.depth; b.n_parents = l.n_parents;
+  b.parents = l.parents; b.roots = l.roots; b.children = l.children; b.n_children = l.n_children; b.cap = l.cap;
+  b.incumbent = l.incumbent; b.leaves = (fqb::LeafRec*)l.leaves; b.n_leaves = l.n_leaves; b.leaf_cap = l.leaf_cap;
+  b.flags = l.flags;
+#define FQ_CASE(NN) case NN: return l.k.force_final ? fqb::launch_level<NN, true>(b, stream) : fqb::launch_level<NN, false>(b, stream);
+  switch (l.k.N)
+  {
+    FQ_CASE(4) FQ_CASE(5) FQ_CASE(6) FQ_CASE(7) FQ_CASE(8) FQ_CASE(9) FQ_CASE(10) FQ_CASE(11) FQ_CASE(12)
+    FQ_CASE(13) FQ_CASE(14) FQ_CASE(15) FQ_CASE(16)
+    default: return cudaErrorInvalidConfiguration;
+  }
+#undef FQ_CASE
 }

@@ -72,3 +72,24 @@ cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaSt
                             bool force_generic = false);
 bool fq_has_specialised(int N, int force_final, int max_faces);
 cudaError_t fq_launch_select(const FqSelectArgs& a, cudaStream_t stream);
+
+// ---- branch-and-bound over assignments (fq_bnb.cuh)
+struct FqBnbLevel
+{
+  FqKernelArgs k;                  // plan + ONE problem
+  int n_dt, P;
+  const double* dts;               // device
+  int depth, n_parents;
+  const unsigned char* parents;
+  const int* roots;
+  unsigned char* children;
+  int* n_children;
+  int cap;
+  unsigned long long* incumbent;
+  void* leaves;                    // fqb::LeafRec[leaf_cap]: {int dt_idx, pad; double cost; uchar sigma[16]}
+  int* n_leaves;
+  int leaf_cap;
+  int* flags;
+};
+size_t fq_bnb_node_bytes(int N, int force_final);     // 0 if unsupported
+cudaError_t fq_launch_bnb_level(const FqBnbLevel& l, cudaStream_t stream);

@@ -201,6 +201,91 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
   }
 }
 
+// Per-lane constants of one (problem, dt): Yeq of the lane's rows and the box thresholds (limit + tol) * dt^k.
+template <class D>
+__device__ __forceinline__ void setup_rows(const FqKernelArgs& a, int prob, double dt, double lim0, double lim1, double lim2,
+                                           int lane, double (&Yeq)[D::RPL][3], double (&bthr)[D::RPL])
+{
+  constexpr int N = D::N, NY = D::NY, NE = D::NE;
+  const double dt2 = dt * dt;
+  {
+    double hdr[3][3 + NE];
+    const double* x0 = a.x0 + prob * 9;
+    const double* xf = a.xf + prob * 9;
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++)
+    {
+      const double s0 = x0[ax], s1 = x0[3 + ax] * dt, s2 = x0[6 + ax] * dt2;
+      hdr[ax][0] = s0; hdr[ax][1] = s1; hdr[ax][2] = s2;
+      double tgt[3];
+      int e = 0;
+      if (NE == 3) tgt[e++] = xf[ax];
+      tgt[e++] = xf[3 + ax] * dt;
+      tgt[e++] = xf[6 + ax] * dt2;
+#pragma unroll
+      for (int k = 0; k < NE; k++)
+        hdr[ax][3 + k] = tgt[k] - fma(a.FT[k * 3 + 0], s0, fma(a.FT[k * 3 + 1], s1, a.FT[k * 3 + 2] * s2));
+    }
+#pragma unroll
+    for (int r = 0; r < D::RPL; r++)
+    {
+      const int y = lane + 32 * r;
+      // box type of the row: v (rows N+1..2N), a (2N+1..3N), j (3N+1..4N), none otherwise
+      bthr[r] = (y >= N + 1 && y <= 2 * N) ? (lim0 + FQ_ROW_TOL) * dt
+                : ((y >= 2 * N + 1 && y <= 3 * N) ? (lim1 + FQ_ROW_TOL) * dt2
+                                                  : ((y >= 3 * N + 1 && y <= 4 * N) ? (lim2 + FQ_ROW_TOL) * dt2 * dt : 1e300));
+#pragma unroll
+      for (int ax = 0; ax < 3; ax++) Yeq[r][ax] = 0.0;
+      if (y < NY)
+      {
+        const double* t0 = a.T0 + y * (3 + NE);
+#pragma unroll
+        for (int k = 0; k < 3 + NE; k++)
+        {
+          const double t = __ldg(t0 + k);
+#pragma unroll
+          for (int ax = 0; ax < 3; ax++) Yeq[r][ax] = fma(t, hdr[ax][k], Yeq[r][ax]);
+        }
+      }
+    }
+  }
+}
+
+// Corridor item list of the first n_seg segments: item = t << 12 | need_cp0 << 11 | face (row of the staged Ab).
+// `p` = polytope of segment `lane` (meaningful for lane < n_seg).  Returns the number of items.
+template <class D>
+__device__ __forceinline__ int build_items(const WarpState<D>& m, const int* __restrict__ sfo, int* __restrict__ seg_ofs,
+                                           int lane, int n_seg, int p)
+{
+  int F = 0;
+  if (lane < n_seg) F = sfo[p + 1] - sfo[p];
+  const int pprev = __shfl_up_sync(FULL, p, 1);
+  const int need0 = (lane == 0 || pprev != p) ? 1 : 0;
+  int incl = F;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total_rows = __shfl_sync(FULL, incl, n_seg - 1);
+  // seg_ofs[t] = first item of segment t; seg_ofs[16 + t] = (need_cp0 << 11) | first staged face of sigma[t]
+  if (lane < n_seg) { seg_ofs[lane] = incl - F; seg_ofs[16 + lane] = (need0 << 11) | sfo[p]; }
+  else if (lane < 16) seg_ofs[lane] = 0x7fffffff;
+  __syncwarp();
+  // item_cap >= N * (faces of the largest polytope) >= total_rows by construction (host side)
+  for (int i = lane; i < total_rows; i += 32)
+  {
+    int t = 0;                                   // largest t with seg_ofs[t] <= i  (N <= 16: 4 halving steps)
+#pragma unroll
+    for (int step = 8; step; step >>= 1)
+      if (seg_ofs[t + step] <= i) t += step;
+    const int meta = seg_ofs[16 + t];
+    m.items[i] = (unsigned short)((t << 12) | (meta + (i - seg_ofs[t])));
+  }
+  return total_rows;
+}
+
 // The dual active-set iteration: from the current state (w, J, R in shared; lam, rdinv, q in registers; Y and the lane's
 // rank key/code already evaluated for the current w) run until no enabled row is violated (returns 1), a violated row
 // cannot be reached (0) or the iteration cap / a NaN is hit (-1).  Enabled rows = box rows + the `total_rows` items of
@@ -442,55 +527,15 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
                                 const int* __restrict__ sfo, const WarpState<D>& m, int* __restrict__ seg_ofs,
                                 int prob, int cand, int lane, bool rows_bad)
 {
-  constexpr int N = D::N, NW = D::NW, NY = D::NY, NYP = D::NYP, LD = D::LD, NE = D::NE, SLOTS = D::SLOTS;
-  const double dt = a.dt[cand], dt2 = dt * dt;
+  constexpr int N = D::N, NW = D::NW, NYP = D::NYP, LD = D::LD, SLOTS = D::SLOTS;
+  const double dt = a.dt[cand];
   const double inv1 = 1.0 / dt, inv2 = inv1 * inv1, inv3 = inv2 * inv1;
   const double lim0 = a.lim[prob * 3 + 0], lim1 = a.lim[prob * 3 + 1], lim2 = a.lim[prob * 3 + 2];
   const int P = a.poly_ofs[prob + 1] - a.poly_ofs[prob];
 
   // ---- per-lane constants of the owned rows: Yeq, box scale and limit
   double Yeq[D::RPL][3], bthr[D::RPL];
-  {
-    double hdr[3][3 + NE];
-    const double* x0 = a.x0 + prob * 9;
-    const double* xf = a.xf + prob * 9;
-#pragma unroll
-    for (int ax = 0; ax < 3; ax++)
-    {
-      const double s0 = x0[ax], s1 = x0[3 + ax] * dt, s2 = x0[6 + ax] * dt2;
-      hdr[ax][0] = s0; hdr[ax][1] = s1; hdr[ax][2] = s2;
-      double tgt[3];
-      int e = 0;
-      if (NE == 3) tgt[e++] = xf[ax];
-      tgt[e++] = xf[3 + ax] * dt;
-      tgt[e++] = xf[6 + ax] * dt2;
-#pragma unroll
-      for (int k = 0; k < NE; k++)
-        hdr[ax][3 + k] = tgt[k] - fma(a.FT[k * 3 + 0], s0, fma(a.FT[k * 3 + 1], s1, a.FT[k * 3 + 2] * s2));
-    }
-#pragma unroll
-    for (int r = 0; r < D::RPL; r++)
-    {
-      const int y = lane + 32 * r;
-      // box type of the row: v (rows N+1..2N), a (2N+1..3N), j (3N+1..4N), none otherwise
-      bthr[r] = (y >= N + 1 && y <= 2 * N) ? (lim0 + FQ_ROW_TOL) * dt
-                : ((y >= 2 * N + 1 && y <= 3 * N) ? (lim1 + FQ_ROW_TOL) * dt2
-                                                  : ((y >= 3 * N + 1 && y <= 4 * N) ? (lim2 + FQ_ROW_TOL) * dt2 * dt : 1e300));
-#pragma unroll
-      for (int ax = 0; ax < 3; ax++) Yeq[r][ax] = 0.0;
-      if (y < NY)
-      {
-        const double* t0 = a.T0 + y * (3 + NE);
-#pragma unroll
-        for (int k = 0; k < 3 + NE; k++)
-        {
-          const double t = __ldg(t0 + k);
-#pragma unroll
-          for (int ax = 0; ax < 3; ax++) Yeq[r][ax] = fma(t, hdr[ax][k], Yeq[r][ax]);
-        }
-      }
-    }
-  }
+  setup_rows<D>(a, prob, dt, lim0, lim1, lim2, lane, Yeq, bthr);
   // ---- non-finite or non-positive inputs (the device-pointer entry cannot be validated on the host): such a
   //      candidate is reported "not solved" right away.  NaN keys would otherwise rank as "satisfied".
   {
@@ -513,41 +558,17 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
       return;
     }
   }
-  // ---- corridor item list: item = t << 12 | need_cp0 << 11 | face (row of the staged Ab)
+  // ---- corridor item list
   int total_rows = 0;
   if (P > 0)
   {
-    int F = 0, p = 0, pprev = -1;
+    int p = 0;
     if (lane < N)
     {
       p = a.sigma[(size_t)cand * N + lane];
       if (p >= P) p = P - 1;
-      F = sfo[p + 1] - sfo[p];
     }
-    pprev = __shfl_up_sync(FULL, p, 1);
-    const int need0 = (lane == 0 || pprev != p) ? 1 : 0;
-    int incl = F;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-      const int v = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    total_rows = __shfl_sync(FULL, incl, N - 1);
-    // seg_ofs[t] = first item of segment t; seg_ofs[16 + t] = (need_cp0 << 11) | first staged face of sigma[t]
-    if (lane < N) { seg_ofs[lane] = incl - F; seg_ofs[16 + lane] = (need0 << 11) | sfo[p]; }
-    else if (lane < 16) seg_ofs[lane] = 0x7fffffff;
-    __syncwarp();
-    // a.item_cap >= N * (faces of the problem) >= total_rows by construction (host side)
-    for (int i = lane; i < total_rows; i += 32)
-    {
-      int t = 0;                                   // largest t with seg_ofs[t] <= i  (N <= 16: 4 halving steps)
-#pragma unroll
-      for (int step = 8; step; step >>= 1)
-        if (seg_ofs[t + step] <= i) t += step;
-      const int meta = seg_ofs[16 + t];
-      m.items[i] = (unsigned short)((t << 12) | (meta + (i - seg_ofs[t])));
-    }
+    total_rows = build_items<D>(m, sfo, seg_ofs, lane, N, p);
   }
   // ---- J = I, w = 0
   for (int idx = lane; idx < NW * LD; idx += 32) m.J[idx] = 0.0;

@@ -107,6 +107,16 @@ int fq_gen_new_traj_sampled(fq_ctx* ctx, int N, int force_final, const double* x
                             const uint8_t* sigmas, double DC, int max_samples, int* dt_index, int* sigma_index,
                             double* cost, double* coeffs, double* samples, int* n_samples);
 
+/* genNewTraj with the EXACT MIQP optimum: the minimum over all P^N interval->polytope assignments for every time
+ * allocation, which is what Gurobi's branch-and-bound over the binaries b[t][p] returns (solverGurobi.cpp:217-246,
+ * :445-472).  Branch-and-bound on the GPU over the segments (dual warm starts from the parent node, bound pruning with the
+ * best non-decreasing assignment as incumbent).  Outputs: winning dt index (-1 none), its assignment sigma_out[N], cost,
+ * coefficients; *nodes_out = nodes evaluated; *exact_out = 0 if the tree had to be cut (node pool overflow, N < 4 or
+ * more than 2047 faces) and the result is the best non-decreasing assignment instead.  Returns 1 / 0 / <0. */
+int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf, const double* lim,
+                          int P, const int* face_ofs, const double* Ab, int n_dt, const double* dts, int* dt_index,
+                          uint8_t* sigma_out, double* cost, double* coeffs, long* nodes_out, int* exact_out);
+
 /* ---- host-side helpers (no GPU needed) ------------------------------------------------------------- */
 
 /* getDTInitial (solverGurobi.cpp:659-759), including its float temporaries and MinPositiveElement

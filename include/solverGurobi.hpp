@@ -46,7 +46,7 @@ public:
 class SolverGurobi
 {
 public:
-  enum AssignmentMode { MONOTONE = 0, ALL = 1, AUTO = 2 };
+  enum AssignmentMode { MONOTONE = 0, ALL = 1, AUTO = 2, EXACT = 3 };
 
   SolverGurobi()
   {
@@ -80,7 +80,9 @@ public:
   //   MONOTONE  the non-decreasing ones only, C(N+P-1, P-1) (identical genNewTraj results in 960/960 measured sweeps,
   //             see DESIGN.md section 2);
   //   AUTO      (default) ALL while P^N <= auto_all_limit (4096: covers the shipped yaml, N=6 and <=3 polytopes: 729),
-  //             MONOTONE beyond.
+  //             MONOTONE beyond;
+  //   EXACT     branch-and-bound over all P^N on the GPU (fq_gen_new_traj_exact): the exact MIQP optimum for any size,
+  //             a few hundred microseconds per sweep instead of ~80.
   void setAssignmentMode(AssignmentMode m, long max_assignments = 16384, long auto_all_limit = 4096)
   {
     amode_ = m; max_sigma_ = max_assignments; auto_all_limit_ = auto_all_limit;
@@ -149,7 +151,18 @@ public:
       const auto t0 = std::chrono::steady_clock::now();
       int dt_idx = -1, sig_idx = -1;
       int rc = FQ_E_NOGPU;
-      if (ensureContext() && ensureAssignments())
+      if (amode_ == EXACT && P_ > 0)
+      {
+        if (ensureContext())
+        {
+          exact_sigma_.assign(N_, 0);
+          rc = fq_gen_new_traj_exact(ctx_, N_, forceFinalConstraint_ ? 1 : 0, x0_, xf_, lims(), P_, face_ofs_.data(), Ab_.data(),
+                                     (int)dts.size(), dts.data(), &dt_idx, exact_sigma_.data(), &cost_, coeffs_buf(), &bnb_nodes_,
+                                     &bnb_exact_);
+          sig_idx = -2;   // assignment held in exact_sigma_
+        }
+      }
+      else if (ensureContext() && ensureAssignments())
         rc = fq_gen_new_traj(ctx_, N_, forceFinalConstraint_ ? 1 : 0, x0_, xf_, lims(), P_, face_ofs_.data(),
                              Ab_.empty() ? nullptr : Ab_.data(), (int)dts.size(), dts.data(), (int)n_sigma_,
                              sigmas_.empty() ? nullptr : sigmas_.data(), &dt_idx, &sig_idx, &cost_, coeffs_buf());
@@ -235,10 +248,14 @@ public:
   std::vector<int> getAssignment() const
   {
     std::vector<int> s;
-    if (sigma_idx_ >= 0 && !sigmas_.empty())
+    if (sigma_idx_ == -2)
+      for (int t = 0; t < N_ && t < (int)exact_sigma_.size(); t++) s.push_back(exact_sigma_[t]);
+    else if (sigma_idx_ >= 0 && !sigmas_.empty())
       for (int t = 0; t < N_; t++) s.push_back(sigmas_[(size_t)sigma_idx_ * N_ + t]);
     return s;
   }
+  long getBnbNodes() const { return bnb_nodes_; }       // EXACT mode: nodes evaluated by the last sweep
+  bool lastSweepExact() const { return bnb_exact_ != 0; }
 
   std::vector<state> X_temp_;
   double dt_ = 0;  // time step found by the solver
@@ -276,7 +293,7 @@ protected:
     if (sig_N_ == N_ && sig_P_ == P_ && sig_mode_ == amode_) return true;
     sigmas_.clear();
     AssignmentMode mode = amode_;
-    if (mode == AUTO) mode = std::pow((double)P_, (double)N_) <= (double)auto_all_limit_ ? ALL : MONOTONE;
+    if (mode == AUTO || mode == EXACT) mode = std::pow((double)P_, (double)N_) <= (double)auto_all_limit_ ? ALL : MONOTONE;
     if (mode == MONOTONE)
     {
       const long total = fq_monotone_sigmas(N_, P_, nullptr, 0);
@@ -321,7 +338,9 @@ protected:
   std::vector<int> face_ofs_{ 0 };
   std::vector<double> Ab_;           // rows [Ax Ay Az b]
   std::vector<double> coeffs_;       // N x 12
-  std::vector<uint8_t> sigmas_;
+  std::vector<uint8_t> sigmas_, exact_sigma_;
+  long bnb_nodes_ = 0;
+  int bnb_exact_ = 1;
   long n_sigma_ = 1, max_sigma_ = 16384, auto_all_limit_ = 4096;
   int sig_N_ = -1, sig_P_ = -1, sig_mode_ = -1, sigma_idx_ = -1;
   AssignmentMode amode_ = AUTO;

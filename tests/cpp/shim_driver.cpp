@@ -26,14 +26,18 @@ int main()
     for (int f = 0; f < F; f++) std::cin >> Am(f, 0) >> Am(f, 1) >> Am(f, 2) >> bm(f);
     polys.push_back(LinearConstraint3D(Am, bm));
   }
+  int mode = -1;
+  if (std::cin >> mode) {}                       // optional trailing token: SolverGurobi::AssignmentMode
   SolverGurobi sg;
+  if (mode >= 0) sg.setAssignmentMode((SolverGurobi::AssignmentMode)mode);
   sg.setN(N); sg.createVars(); sg.setDC(DC); sg.setBounds(lim); sg.setForceFinalConstraint(ff != 0);
   sg.setFactorInitialAndFinalAndIncrement(fi, fl, finc); sg.setVerbose(0); sg.setThreads(0); sg.setWMax(4.0);
   sg.ResetToNormalState();
   sg.setX0(A); sg.setXf(E); sg.setPolytopes(polys);
   bool solved = sg.genNewTraj();
-  std::printf("{\"solved\": %d, \"trials\": %d, \"dt\": %.17g, \"factor\": %.17g, \"cost\": %.17g, \"n_samples\": %zu, \"runtime_ms\": %.3f",
-              solved ? 1 : 0, sg.trials_, sg.dt_, sg.factor_that_worked_, solved ? sg.getCost() : -1.0, sg.X_temp_.size(), sg.runtime_ms_);
+  std::printf("{\"mode\": %d, \"bnb_nodes\": %ld, \"exact\": %d, \"solved\": %d, \"trials\": %d, \"dt\": %.17g, \"factor\": %.17g, \"cost\": %.17g, \"n_samples\": %zu, \"runtime_ms\": %.3f",
+              mode, sg.getBnbNodes(), sg.lastSweepExact() ? 1 : 0, solved ? 1 : 0, sg.trials_, sg.dt_, sg.factor_that_worked_,
+              solved ? sg.getCost() : -1.0, sg.X_temp_.size(), sg.runtime_ms_);
   if (solved)
   {
     sg.fillX();

@@ -503,3 +503,43 @@ def test_huge_polytopes_fall_back_to_generic_kernel(solver, oracle):
     fg, cg, cog, _ = solver.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], fat, dts, sigs, True, True)
     fo, co_, coo = oracle.solve_batch(10, pb["x0"], pb["xf"], pb["lim"], fat, dts, sigs, True, True, threads=8)
     _compare(fg, cg, cog, fo, co_, coo, "700-face polytopes")
+
+
+def test_exact_miqp_branch_and_bound_on_gpu(solver, oracle):
+    """fq_gen_new_traj_exact (GPU branch-and-bound over all P^N assignments) against the oracle's branch-and-bound:
+    per time allocation (incl. the known cases where the best non-decreasing assignment is NOT optimal) and as a sweep."""
+    # (seed, N, P, force_final, factor): the three non-monotone optima found by the round-1 study + ordinary cases
+    cases = [(5007, 10, 3, True, 5.0), (5007, 6, 3, True, 5.0), (5055, 10, 4, False, 5.0)]
+    cases += [(5000 + s, N, P, ff, f) for s in range(6) for (N, P, ff) in ((10, 3, True), (10, 4, False), (6, 3, False)) for f in (2.0, 3.0)]
+    n_nonmono = 0
+    for seed, N, P, ff, f in cases:
+        pb = cr.make_corridor(seed, P, N, "uav", ff)
+        dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N)
+        dt = f * max(dti, 0.02)
+        g = solver.gen_new_traj_exact(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], [dt], ff)
+        rc, c, co, sg, nodes = oracle.solve_miqp(N, pb["x0"], pb["xf"], pb["lim"], dt, pb["polys"], ff)
+        assert g["exact"], (seed, N, P)
+        assert g["solved"] == (rc == 1), (seed, N, P, f)
+        if rc == 1:
+            assert abs(g["cost"] - c) <= REL * max(1.0, c), (seed, N, P, f, g["cost"], c)
+            assert np.abs(g["coeffs"] - co).max() <= 1e-6 * max(1.0, np.abs(co).max())
+            if np.any(np.diff(g["sigma"].astype(int)) < 0):
+                n_nonmono += 1
+            # the returned assignment really attains the cost
+            r2, c2, _, _ = oracle.solve_fixed(N, pb["x0"], pb["xf"], pb["lim"], dt, pb["polys"], g["sigma"], ff)
+            assert r2 == 1 and abs(c2 - c) <= 1e-9 * max(1.0, c)
+    assert n_nonmono >= 2          # the study's cases are reproduced: the exact optimum is not monotone there
+    # sweeps (first feasible factor wins) on synthetic and forest corridors
+    for seed in range(8):
+        for kind in ("synthetic", "forest"):
+            try:
+                pb = cr.make_corridor(7000 + seed, 3, 10) if kind == "synthetic" else cr.make_forest_corridor(7100 + seed, 3, 10, True)
+            except RuntimeError:
+                continue
+            dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], 10)
+            dts = np.arange(1.0, 11.0) * max(dti, 0.02)
+            g = solver.gen_new_traj_exact(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, True)
+            o = oracle.gen_new_traj(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], 0.01, 1.0, 10.0, 1.0, None, True)
+            assert g["exact"] and g["solved"] == o["solved"]
+            if o["solved"]:
+                assert g["dt_index"] + 1 == o["trials"] and abs(g["cost"] - o["cost"]) <= REL * max(1.0, o["cost"])

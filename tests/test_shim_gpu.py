@@ -22,12 +22,14 @@ def driver(built_lib, tmp_path_factory):
     return exe
 
 
-def _run(exe, N, ff, DC, lim, fi, fl, finc, x0, xf, polys):
+def _run(exe, N, ff, DC, lim, fi, fl, finc, x0, xf, polys, mode=None):
     toks = [N, int(ff), DC, *lim, fi, fl, finc, *x0, *xf, len(polys)]
     for A, b in polys:
         toks.append(len(b))
         for f in range(len(b)):
             toks += [*A[f], b[f]]
+    if mode is not None:
+        toks.append(int(mode))
     out = subprocess.run([exe], input=" ".join(repr(float(t)) if isinstance(t, (float, np.floating)) else str(t) for t in toks),
                          capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
@@ -157,3 +159,24 @@ def test_replan_sequence_with_drop_in_class(replan_driver, oracle):
             if "R" in e:
                 assert np.allclose(g["safe"]["x0"], e["R"], atol=1e-7)
     assert compared >= 8
+
+
+@pytest.mark.gpu
+def test_shim_exact_mode_matches_oracle(driver, oracle, demo_corridor):
+    """setAssignmentMode(EXACT): branch-and-bound on the GPU behind the drop-in class (N=10, P=3: 59 049 assignments)."""
+    fx = demo_corridor
+    cases = [(fx["N"], True, fx["x0"], fx["xf"], fx["lim"], fx["polys"])]
+    for seed in range(3):
+        pb = cr.make_corridor(640 + seed, 4, 10, force_final=False)
+        cases.append((10, False, pb["x0"], pb["xf"], pb["lim"], pb["polys"]))
+    for N, ff, x0, xf, lim, polys in cases:
+        r = _run(driver, N, ff, 0.01, lim, 1.0, 10.0, 1.0, x0, xf, polys, mode=3)
+        o = oracle.gen_new_traj(N, x0, xf, lim, polys, 0.01, 1.0, 10.0, 1.0, None, ff)
+        assert r["mode"] == 3 and r["exact"] == 1
+        assert bool(r["solved"]) == o["solved"] and r["trials"] == o["trials"]
+        if o["solved"]:
+            assert r["bnb_nodes"] > 0 and r["factor"] == o["factor"]
+            assert abs(r["cost"] - o["cost"]) <= 1e-7 * max(1.0, o["cost"])
+            co = np.array(r["coeffs"]).reshape(N, 12)
+            assert np.abs(co - o["coeffs"]).max() <= 1e-6 * max(1.0, np.abs(o["coeffs"]).max())
+            assert len(r["assignment"]) == N

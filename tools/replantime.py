@@ -18,3 +18,13 @@ def host():
 def dev():
     return s.gen_new_traj_sampled(10,pb["x0"],pb["xf"],pb["lim"],pb["polys"],dts,sig,0.01,True,max_samples=1024)["X"]
 print('genNewTraj+fillX: host sampling %.1f us, device sampling %.1f us, samples %d' % (timeit(host), timeit(dev), len(host())))
+def exact():
+    return s.gen_new_traj_exact(10,pb["x0"],pb["xf"],pb["lim"],pb["polys"],dts,True)
+g=exact()
+print('exact sweep: %.1f us, nodes %d, exact %s, dt_index %d' % (timeit(exact, 100), g['nodes'], g['exact'], g['dt_index']))
+# a loose time allocation (factor 5): bigger tree
+dts5=np.array([5.0*max(dti,0.02)])
+def exact5():
+    return s.gen_new_traj_exact(10,pb["x0"],pb["xf"],pb["lim"],pb["polys"],dts5,True)
+g=exact5()
+print('exact single dt (factor 5): %.1f us, nodes %d' % (timeit(exact5, 50), g['nodes']))
