@@ -288,6 +288,12 @@ def main():
         g = solver.gen_new_traj(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts10, sig66, True)
         lat.append(time.perf_counter() - t0)
     replan_us = float(np.median(lat[10:]) * 1e6)
+    lat = []
+    for i in range(40):
+        t0 = time.perf_counter()
+        ge = solver.gen_new_traj_exact(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts10, True)
+        lat.append(time.perf_counter() - t0)
+    replan_exact_us = float(np.median(lat[10:]) * 1e6)
 
     t = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -335,7 +341,8 @@ def main():
                            "e2e_matches_resident": same},
                 "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": 2 * args.steps,
-                "replan_latency_us": {"value": replan_us, "what": "fq_gen_new_traj: 10 factors x 66 assignments, N=10, P=3, host in/out, median of 50"},
+                "replan_latency_us": {"value": replan_us, "what": "fq_gen_new_traj: 10 factors x 66 assignments, N=10, P=3, host in/out, median of 50",
+                                      "exact_miqp": replan_exact_us, "exact_nodes": int(ge["nodes"]), "exact_same_winner": bool(ge["dt_index"] == g["dt_index"] and abs(ge["cost"] - g["cost"]) <= 1e-9 * max(1.0, g["cost"]))},
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": prof.get("traffic"), "kernel": "fq_solve_kernel_t<10,*>", "kernel_ms": kernel_ms,
