@@ -79,10 +79,10 @@ public:
   //   ALL       every one of the P^N (the exact MIQP optimum, like Gurobi's branch-and-bound);
   //   MONOTONE  the non-decreasing ones only, C(N+P-1, P-1) (identical genNewTraj results in 960/960 measured sweeps,
   //             see DESIGN.md section 2);
-  //   AUTO      (default) ALL while P^N <= auto_all_limit (4096: covers the shipped yaml, N=6 and <=3 polytopes: 729),
-  //             MONOTONE beyond;
   //   EXACT     branch-and-bound over all P^N on the GPU (fq_gen_new_traj_exact): the exact MIQP optimum for any size,
-  //             a few hundred microseconds per sweep instead of ~80.
+  //             ~160 us per sweep instead of ~80;
+  //   AUTO      (default) ALL while P^N <= auto_all_limit (4096: covers the shipped yaml, N=6 and <=3 polytopes: 729),
+  //             EXACT beyond -- i.e. always the reference's MIQP optimum.
   void setAssignmentMode(AssignmentMode m, long max_assignments = 16384, long auto_all_limit = 4096)
   {
     amode_ = m; max_sigma_ = max_assignments; auto_all_limit_ = auto_all_limit;
@@ -151,7 +151,8 @@ public:
       const auto t0 = std::chrono::steady_clock::now();
       int dt_idx = -1, sig_idx = -1;
       int rc = FQ_E_NOGPU;
-      if (amode_ == EXACT && P_ > 0)
+      const bool small_enum = std::pow((double)P_, (double)N_) <= (double)auto_all_limit_;
+      if ((amode_ == EXACT || (amode_ == AUTO && !small_enum)) && P_ > 0)
       {
         if (ensureContext())
         {
