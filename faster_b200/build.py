@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfaster_b200.so")
-SOURCES = ["fq_kernels.cu", "fq_capi.cu", "fq_host.cpp", "fq_decomp.cpp"]
+SOURCES = ["fq_kernels.cu", "fq_capi.cu", "fq_host.cpp", "fq_decomp.cpp", "fq_jps.cpp"]
 HEADERS = ["fq_kernels.cuh", "fq_plan.h", os.path.join("..", "..", "include", "faster_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-cudart", "static"]

@@ -12,7 +12,7 @@ _lib = None
 
 EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_set_option", "fq_solve_batch", "fq_solve_multi",
            "fq_solve_multi_dev", "fq_gen_new_traj", "fq_gen_new_traj_sampled", "fq_gen_new_traj_exact", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
-           "fq_monotone_sigmas", "fq_plan_tables", "fq_ellipsoid_decomp"]
+           "fq_monotone_sigmas", "fq_plan_tables", "fq_ellipsoid_decomp", "fq_jps3d_plan", "fq_jps3d_plan_world", "fq_jps3d_rules"]
 
 
 class FqError(RuntimeError):
@@ -114,6 +114,58 @@ def ellipsoid_decomp(path, obs, bbox=(2.0, 2.0, 1.0), inflate=0.42, z_ground=0.0
     if rows < 0:
         raise FqError("fq_ellipsoid_decomp failed (%d)" % rows)
     return [(Ab[ofs[i]:ofs[i + 1], :3].copy(), Ab[ofs[i]:ofs[i + 1], 3].copy()) for i in range(n_seg)]
+
+
+def jps3d_plan(grid, start, goal, use_jps=True, max_expand=-1):
+    """grid: int8 array [zd, yd, xd] (x fastest in memory).  -> (path int[n,3] (x,y,z), cost in cells, expanded)."""
+    g = np.ascontiguousarray(grid, np.int8)
+    zd, yd, xd = g.shape
+    s = np.asarray(start, np.int32).copy()
+    t = np.asarray(goal, np.int32).copy()
+    cap = 4 * (xd + yd + zd) + 16
+    out = np.zeros((cap, 3), np.int32)
+    cost, ex = C.c_double(np.inf), C.c_int(0)
+    L = lib()
+    L.fq_jps3d_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                C.c_int, C.c_void_p, C.c_void_p]
+    n = L.fq_jps3d_plan(g.ctypes.data, xd, yd, zd, s.ctypes.data, t.ctypes.data, int(use_jps), int(max_expand),
+                        out.ctypes.data, cap, C.addressof(cost), C.addressof(ex))
+    if n < 0:
+        raise FqError("fq_jps3d_plan failed (%d)" % n)
+    if n > cap:
+        out = np.zeros((n, 3), np.int32)
+        n = L.fq_jps3d_plan(g.ctypes.data, xd, yd, zd, s.ctypes.data, t.ctypes.data, int(use_jps), int(max_expand),
+                            out.ctypes.data, n, C.addressof(cost), C.addressof(ex))
+    return out[:n].copy(), cost.value, ex.value
+
+
+def jps3d_plan_world(grid, origin, res, start, goal, use_jps=True, cap=4096):
+    """World-coordinate plan with the reference's post-processing -> (path float[n,3], raw_cost in metres)."""
+    g = np.ascontiguousarray(grid, np.int8)
+    zd, yd, xd = g.shape
+    o, s, t = _f64(origin, 3), _f64(start, 3), _f64(goal, 3)
+    out = np.zeros((cap, 3))
+    rc = C.c_double(np.inf)
+    L = lib()
+    L.fq_jps3d_plan_world.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    n = L.fq_jps3d_plan_world(g.ctypes.data, xd, yd, zd, o.ctypes.data, float(res), s.ctypes.data, t.ctypes.data,
+                              int(use_jps), out.ctypes.data, cap, C.addressof(rc))
+    if n < 0:
+        raise FqError("fq_jps3d_plan_world failed (%d)" % n)
+    return out[:n].copy(), rc.value
+
+
+def jps3d_rules():
+    ns = np.zeros((27, 3, 26), np.int32)
+    f1 = np.zeros((27, 3, 12), np.int32)
+    f2 = np.zeros((27, 3, 12), np.int32)
+    cnt = np.zeros((27, 2), np.int32)
+    L = lib()
+    L.fq_jps3d_rules.argtypes = [C.c_void_p] * 4
+    L.fq_jps3d_rules.restype = None
+    L.fq_jps3d_rules(ns.ctypes.data, f1.ctypes.data, f2.ctypes.data, cnt.ctypes.data)
+    return ns, f1, f2, cnt
 
 
 def plan_tables(N, force_final):

@@ -168,3 +168,70 @@ def make_forest_corridor(seed, P, N, force_final=True, decomp=None, DC=0.01, n_t
     xf[:3] = verts[-1]
     return dict(N=N, P=P, x0=x0, xf=xf, lim=np.array(prof["lim"]), polys=polys, force_final=bool(force_final), DC=DC,
                 verts=verts, obs=obs, seed=seed, profile="uav")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The whole input side on the host, as Faster::replan() chains it (faster.cpp:361-398): voxel map -> JPS3D path ->
+# vertices at most dist_max_vertexes apart, at most max_poly segments -> convex decomposition -> polytopes.
+# ------------------------------------------------------------------------------------------------------------------
+def voxelise_forest(centres, radii, area=16.0, height=3.0, res=0.15, inflation=0.0):
+    """Occupancy grid [zd,yd,xd] (int8: 0 free, 100 occupied) of vertical cylinders, origin at (-area/2,-area/2,0)."""
+    n = int(round(area / res))
+    zd = int(round(height / res))
+    xs = (np.arange(n) + 0.5) * res - area / 2
+    X, Y = np.meshgrid(xs, xs)
+    occ = np.zeros((n, n), bool)
+    for c, r in zip(centres, radii):
+        occ |= (X - c[0]) ** 2 + (Y - c[1]) ** 2 <= (r + inflation) ** 2
+    g = np.zeros((zd, n, n), np.int8)
+    g[:, occ] = 100
+    return g, np.array([-area / 2, -area / 2, 0.0]), res
+
+
+def split_long_segments(path, max_len):
+    """createMoreVertexes (faster.cpp:80-97): subdivide segments longer than max_len evenly."""
+    out = [path[0]]
+    for a, b in zip(path[:-1], path[1:]):
+        k = int(np.ceil(np.linalg.norm(b - a) / max_len))
+        for i in range(1, k + 1):
+            out.append(a + (b - a) * (i / k))
+    return np.array(out)
+
+
+def make_jps_forest_corridor(seed, P, N, force_final=True, DC=0.01, n_trees=60):
+    """Corridor problem produced by the product's own host pipeline: fq_jps3d_plan_world on the voxelised forest (obstacles
+    inflated by inflation_jps = 0.47, faster.yaml:20), vertices <= 1.5 m apart (dist_max_vertexes), first P segments,
+    fq_ellipsoid_decomp against the occupied cell centres (the reference decomposes against its occupied cloud)."""
+    from . import capi
+    prof = UAV
+    rng = np.random.default_rng(seed)
+    _, centres, radii = make_forest(seed, n_trees=n_trees)
+    grid_jps, origin, res = voxelise_forest(centres, radii, inflation=0.47)
+    grid, _, _ = voxelise_forest(centres, radii)
+    zd, yd, xd = grid.shape
+    for _ in range(200):
+        s = np.array([rng.uniform(-6, 6), rng.uniform(-6, 6), rng.uniform(0.8, 1.4)])
+        t = s + rng.uniform(3.5, 5.0) * np.array([np.cos(a := rng.uniform(-np.pi, np.pi)), np.sin(a), 0.0])
+        t[2] = rng.uniform(0.8, 1.4)
+        if np.abs(t[:2]).max() > 7.5:
+            continue
+        path, _ = capi.jps3d_plan_world(grid_jps, origin, res, s, t, True)
+        if len(path) >= 2:
+            break
+    else:
+        raise RuntimeError("no path found")
+    verts = split_long_segments(path, 1.5)[:P + 1]
+    if len(verts) < P + 1:
+        raise RuntimeError("path too short for %d polytopes" % P)
+    occ = np.argwhere(grid > 0)[:, ::-1]                       # (x, y, z) cells
+    obs = (occ + 0.5) * res + origin
+    polys = capi.ellipsoid_decomp(verts, obs, prof["bbox"], prof["drone_radius"], prof["z_ground"], cap_rows=8192)
+    d0 = verts[1] - verts[0]
+    d0 /= np.linalg.norm(d0)
+    x0 = np.zeros(9)
+    x0[:3] = verts[0]
+    x0[3:6] = d0 * rng.uniform(*prof["v0"])
+    xf = np.zeros(9)
+    xf[:3] = verts[-1]
+    return dict(N=N, P=P, x0=x0, xf=xf, lim=np.array(prof["lim"]), polys=polys, force_final=bool(force_final), DC=DC,
+                verts=verts, obs=obs, seed=seed, profile="uav", jps_path=path)

@@ -144,6 +144,26 @@ long fq_monotone_sigmas(int N, int P, uint8_t* out, long cap);
 int fq_ellipsoid_decomp(const double* path, int n_seg, const double* obs, int n_obs, const double* bbox,
                         double inflate, double z_ground, int* face_ofs, double* Ab, int cap_rows);
 
+/* Path search on a voxel grid -- the host-side input generator in front of the decomposition
+ * (jps_manager_.solveJPS3D, faster.cpp:361 -> thirdparty/jps3d GraphSearch, graph_search.cpp:123-219,:272-470).
+ * map: xd*yd*zd cells, x fastest; 0 free, > 0 occupied, < 0 unknown.  26-connected, Euclidean costs and heuristic;
+ * use_jps != 0: jump point search, else plain A*.  path_out receives up to cap (x,y,z) cell triples from start to goal
+ * (jump points only with JPS).  Returns the number of path points (0: no path / start or goal not free), <0 on error;
+ * *cost = path length in cells, *n_expanded = nodes expanded.  Pure host code. */
+int fq_jps3d_plan(const int8_t* map, int xd, int yd, int zd, const int* start, const int* goal, int use_jps,
+                  int max_expand, int* path_out, int cap, double* cost, int* n_expanded);
+
+/* The same in world coordinates with the reference's post-processing (JPSPlanner<3>::plan, jps_planner.cpp:196-295:
+ * cell = round((p - origin)/res - 0.5), centre = (cell + 0.5) res + origin (map_util.h:334-347), then removeLinePts and
+ * removeCornerPts forwards and backwards with ray-traced line of sight (jps_planner.cpp:36-105, map_util.h:349-383)).
+ * path_out: up to cap (x,y,z) points.  Returns the number of points, 0 if no path, <0 on error (FQ_E_NOMEM: cap). */
+int fq_jps3d_plan_world(const int8_t* map, int xd, int yd, int zd, const double* origin, double res, const double* start,
+                        const double* goal, int use_jps, double* path_out, int cap, double* raw_cost);
+
+/* Introspection (tests): the pruning rules in the layout of the reference's JPS3DNeib (graph_search.h:104-136):
+ * ns[27][3][26], f1[27][3][12], f2[27][3][12], counts[27][2] = (natural, forced) entries per direction id. */
+void fq_jps3d_rules(int* ns, int* f1, int* f2, int* counts);
+
 /* Introspection (tests): copies the per-(N, force_final) plan tables documented in faster_b200/csrc/fq_plan.h.
  * Returns NY = 6N+1, or 0 if (N, force_final) is unsupported.  TZ: NY*(N-ne), T0: NY*(3+ne), FT: ne*3,
  * ne = force_final ? 3 : 2.  Any pointer may be NULL. */

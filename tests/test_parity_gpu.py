@@ -543,3 +543,35 @@ def test_exact_miqp_branch_and_bound_on_gpu(solver, oracle):
             assert g["exact"] and g["solved"] == o["solved"]
             if o["solved"]:
                 assert g["dt_index"] + 1 == o["trials"] and abs(g["cost"] - o["cost"]) <= REL * max(1.0, o["cost"])
+
+
+def test_full_host_pipeline_then_gpu_solve(solver, oracle):
+    """BASELINE config 4's chain with the product's own host code at every step: voxelised random forest ->
+    fq_jps3d_plan_world -> fq_ellipsoid_decomp -> exact whole sweep on the GPU; checked against the numpy decomposition
+    oracle and the solver oracle (branch-and-bound over all assignments) on the same JPS path."""
+    from oracle import decomp_oracle as do
+    n = 0
+    for seed in range(500, 510):
+        try:
+            pb = cr.make_jps_forest_corridor(seed, 3, 10)
+        except RuntimeError:
+            continue
+        polys_o = do.cvx_ellipsoid_decomp(pb["verts"], pb["obs"], (2.0, 2.0, 1.0), 0.42, 0.0)
+        for (A1, b1), (A2, b2) in zip(pb["polys"], polys_o):
+            assert A1.shape == A2.shape
+            r1 = np.hstack([A1, b1[:, None]]); r2 = np.hstack([A2, b2[:, None]])
+            r1 = r1[np.lexsort(np.round(r1, 7).T[::-1])]; r2 = r2[np.lexsort(np.round(r2, 7).T[::-1])]
+            assert np.abs(r1 - r2).max() <= 1e-9
+        dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], 10)
+        dts = np.arange(1.0, 11.0) * max(dti, 0.02)
+        g = solver.gen_new_traj_exact(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, True)
+        o = oracle.gen_new_traj(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], 0.01, 1.0, 10.0, 1.0, None, True)
+        assert g["exact"] and g["solved"] == o["solved"]
+        if o["solved"]:
+            assert g["dt_index"] + 1 == o["trials"] and abs(g["cost"] - o["cost"]) <= REL * max(1.0, o["cost"])
+            # the solved trajectory stays clear of the (un-inflated) obstacle cells by the drone radius along its knots
+            X = capi.fill_x(10, g["coeffs"], dts[g["dt_index"]], 0.01)[::10, :3]
+            d = np.linalg.norm(pb["obs"][None, :, :] - X[:, None, :], axis=2).min()
+            assert d > 0.3
+            n += 1
+    assert n >= 5
