@@ -295,6 +295,41 @@ def main():
         lat.append(time.perf_counter() - t0)
     replan_exact_us = float(np.median(lat[10:]) * 1e6)
 
+    # the whole replan input chain with the product's own host code: voxel map -> JPS3D -> convex decomposition ->
+    # exact sweep on the GPU (BASELINE config 4's pipeline), median over a few random forests
+    pipe = {"jps_us": [], "decomp_us": [], "sweep_exact_us": []}
+    if rank == 0:
+        for sd in range(12):
+            try:
+                _, centres, radii = cr.make_forest(3000 + sd)
+                grid_j, origin, res = cr.voxelise_forest(centres, radii, inflation=0.47)
+                grid_o, _, _ = cr.voxelise_forest(centres, radii)
+                rng = np.random.default_rng(sd)
+                s0 = np.array([rng.uniform(-6, 6), rng.uniform(-6, 6), 1.0])
+                ang = rng.uniform(-np.pi, np.pi)
+                t1 = s0 + 4.0 * np.array([np.cos(ang), np.sin(ang), 0.0])
+                t0 = time.perf_counter()
+                path, _ = capi.jps3d_plan_world(grid_j, origin, res, s0, t1, True)
+                tj = time.perf_counter() - t0
+                if len(path) < 2:
+                    continue
+                verts = cr.split_long_segments(path, 1.5)[:4]
+                obs = (np.argwhere(grid_o > 0)[:, ::-1] + 0.5) * res + origin
+                t0 = time.perf_counter()
+                polys = capi.ellipsoid_decomp(verts, obs, (2.0, 2.0, 1.0), 0.42, 0.0, cap_rows=8192)
+                td = time.perf_counter() - t0
+                x0p = np.concatenate([verts[0], np.zeros(6)]); xfp = np.concatenate([verts[-1], np.zeros(6)])
+                dtp = np.arange(1.0, 11.0) * max(capi.dt_initial(x0p, xfp, [5.0, 5.0, 8.0], N_SEG), 0.02)
+                solver.gen_new_traj_exact(N_SEG, x0p, xfp, [5.0, 5.0, 8.0], polys, dtp, True)
+                t0 = time.perf_counter()
+                solver.gen_new_traj_exact(N_SEG, x0p, xfp, [5.0, 5.0, 8.0], polys, dtp, True)
+                ts = time.perf_counter() - t0
+                pipe["jps_us"].append(tj * 1e6); pipe["decomp_us"].append(td * 1e6); pipe["sweep_exact_us"].append(ts * 1e6)
+            except Exception:
+                continue
+    pipeline = {k: (float(np.median(v)) if v else None) for k, v in pipe.items()}
+    pipeline["what"] = "random forest 16 m x 16 m x 3 m at 0.15 m (107x107x20 cells, ~7 k occupied cells), 4 m query, <= 3 polytopes"
+
     t = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -341,6 +376,7 @@ def main():
                            "e2e_matches_resident": same},
                 "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": 2 * args.steps,
+                "replan_pipeline_us": pipeline,
                 "replan_latency_us": {"value": replan_us, "what": "fq_gen_new_traj: 10 factors x 66 assignments, N=10, P=3, host in/out, median of 50",
                                       "exact_miqp": replan_exact_us, "exact_nodes": int(ge["nodes"]), "exact_same_winner": bool(ge["dt_index"] == g["dt_index"] and abs(ge["cost"] - g["cost"]) <= 1e-9 * max(1.0, g["cost"]))},
                 "clocks": sampler.summary(),
