@@ -1,6 +1,6 @@
-// Work-alike of the `state` carrier of reference faster/include/faster_types.hpp:79-165 (same member names and
-// setters), for building solverGurobi.hpp without the reference tree.  When dropping solverGurobi.hpp into the
-// reference, keep the reference's own faster_types.hpp: this file is then not used.
+// Stand-in for the `state` carrier (reference faster/include/faster_types.hpp:79-165: pos/vel/accel/jerk + yaw, with the
+// setters the planner uses), so that solverGurobi.hpp builds and is tested without the reference tree.  Inside the
+// reference tree solverGurobi.hpp finds the reference's own faster_types.hpp first and this file is not used.
 #pragma once
 #if __has_include(<Eigen/Dense>)
 #include <Eigen/Dense>

@@ -16,7 +16,11 @@
 #define SOLVER_GUROBI_HPP
 
 #include "faster_b200.h"
-#include "faster_types.hpp"
+#if __has_include("faster_types.hpp")
+#include "faster_types.hpp"        // the reference's own `state` when this header lives in the reference tree
+#else
+#include "fq_state_compat.hpp"
+#endif
 
 #if __has_include(<decomp_geometry/polyhedron.h>)
 #include <decomp_geometry/polyhedron.h>
