@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
     m.Y = p;   p += 3 * NYP;
     m.w = p;   p += NW;
     m.d = p;   p += NW + 2;
+    m.zb = p;  p += NW;
     m.items = reinterpret_cast<unsigned short*>(p);
     seg_ofs = sfo + 40 + warp * 32;
   }
@@ -155,14 +156,12 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
 #pragma unroll
   for (int s = 0; s < SLOTS; s++) { lam[s] = 0; rdinv[s] = 0; }
   if (k == 0)
-  {
-    for (int idx = lane; idx < NW * LD; idx += 32) m.J[idx] = 0.0;
-    __syncwarp();
+  { // roots: empty factorisation
 #pragma unroll
     for (int s = 0; s < SLOTS; s++)
     {
       const int j = lane + 32 * s;
-      if (j < NW) { m.J[j * LD + j] = 1.0; m.w[j] = 0.0; }
+      if (j < NW) m.w[j] = 0.0;
     }
   }
   else

@@ -10,6 +10,10 @@
 //   * the entering row is the one farthest beyond its hyperplane in w-space: rank = (violation - tol) / |TZ[y]|, compared
 //     through the hi word of that double as a signed int (positive <=> violated), so the warp arg-max is one redux.sync
 //     plus a ballot.  This "normalised pivoting" halves the iteration count relative to "largest violation";
+//   * THIN factorisation: only J1 (NW x q, an orthonormal basis of the active normals, N = J1 R) is kept instead of the
+//     full orthogonal J of the generic kernel.  The projection of a row normal g is z = -(g - J1 J1' g) (q columns, not
+//     NW - q), a new active row appends one column -z/|z| (Gram-Schmidt, with one re-orthogonalisation pass when
+//     |z|^2 < 0.01 |g|^2), nothing has to be initialised per candidate, and leaving rows rotate columns as before;
 //   * duals, the triangular solve and the ratio test are register/shuffle based (element k of an NW-vector lives in
 //     lane k%32, slot k/32); reciprocals and square roots use the MUFU seed + Newton steps instead of IEEE division;
 //   * persistent CTAs: per-problem claim counters in global memory; a CTA adopts a problem that still has unclaimed
@@ -39,7 +43,7 @@ struct Dims
   static constexpr int TZLD = NZ | 1;            // odd row stride of TZ in shared memory
   static constexpr int SLOTS = (NW + 31) / 32;   // elements of an NW-vector per lane
   static constexpr int RPL = (NY + 31) / 32;     // Y rows per lane
-  static constexpr int PER_WARP_DOUBLES = 2 * NW * LD + 3 * NYP + 2 * NW + 2;
+  static constexpr int PER_WARP_DOUBLES = 2 * NW * LD + 3 * NYP + 3 * NW + 2;
 };
 // per-warp bytes: solver state + item list (item_cap 16-bit entries)
 template <class D>
@@ -84,6 +88,7 @@ struct WarpState
   double* Y;            // 3 x NYP
   double* w;            // NW
   double* d;            // NW
+  double* zb;           // NW: scratch for the re-orthogonalisation pass
   unsigned short* items;
 };
 
@@ -365,25 +370,29 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
     {
       if (++it > FQ_MAX_ITERS) { status = -1; break; }
       const double viol = fma(w0, m.Y[y], fma(w1, m.Y[NYP + y], fma(w2, m.Y[2 * NYP + y], -h)));
-      // ---- d = J' g with g = (w0, w1, w2) (x) TZ[y];  zz = |d2|^2
-      double zzp = 0;
+      // ---- thin factorisation: J1 = first q columns of J, an orthonormal basis of the active normals (N = J1 R).
+      //      d1 = J1' g with g = (w0, w1, w2) (x) TZ[y];  z = -(g - J1 d1) = minus the part of g outside span(J1)
+      double gi[SLOTS];
       {
         double s0[SLOTS], s1[SLOTS], s2[SLOTS];
 #pragma unroll
         for (int s = 0; s < SLOTS; s++) { s0[s] = 0; s1[s] = 0; s2[s] = 0; }
-#pragma unroll
-        for (int k = 0; k < NZ; k++)
+        if (q > 0)
         {
-          const double tk = TZ[y * D::TZLD + k];
 #pragma unroll
-          for (int s = 0; s < SLOTS; s++)
+          for (int k = 0; k < NZ; k++)
           {
-            const int j = lane + 32 * s;
-            if (j < NW)
+            const double tk = TZ[y * D::TZLD + k];
+#pragma unroll
+            for (int s = 0; s < SLOTS; s++)
             {
-              s0[s] = fma(tk, m.J[k * LD + j], s0[s]);
-              s1[s] = fma(tk, m.J[(NZ + k) * LD + j], s1[s]);
-              s2[s] = fma(tk, m.J[(2 * NZ + k) * LD + j], s2[s]);
+              const int j = lane + 32 * s;
+              if (j < q)
+              {
+                s0[s] = fma(tk, m.J[k * LD + j], s0[s]);
+                s1[s] = fma(tk, m.J[(NZ + k) * LD + j], s1[s]);
+                s2[s] = fma(tk, m.J[(2 * NZ + k) * LD + j], s2[s]);
+              }
             }
           }
         }
@@ -392,34 +401,83 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
         {
           const int j = lane + 32 * s;
           dreg[s] = fma(w0, s0[s], fma(w1, s1[s], w2 * s2[s]));
-          if (j < NW)
-          {
-            m.d[j] = dreg[s];
-            if (j >= q) zzp = fma(dreg[s], dreg[s], zzp);
-          }
+          if (j < q) m.d[j] = dreg[s];
+          // this lane's component of g: variable j = (axis, column) of the plan table
+          const int ax = j / NZ, kk = j - ax * NZ;
+          gi[s] = j < NW ? (ax == 0 ? w0 : (ax == 1 ? w1 : w2)) * TZ[y * D::TZLD + kk] : 0.0;
         }
       }
       __syncwarp();
-      // ---- z = -J2 d2 (lane-owned rows)
+      double zzp = 0;
 #pragma unroll
       for (int s = 0; s < SLOTS; s++)
       {
         const int i = lane + 32 * s;
-        double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+        double acc0 = -gi[s], acc1 = 0;
         if (i < NW)
         {
           const double* Ji = m.J + i * LD;
-          int j = q;
-          for (; j + 3 < NW; j += 4)
+          int k = 0;
+          for (; k + 1 < q; k += 2)
           {
-            acc0 = fma(Ji[j], m.d[j], acc0);
-            acc1 = fma(Ji[j + 1], m.d[j + 1], acc1);
-            acc2 = fma(Ji[j + 2], m.d[j + 2], acc2);
-            acc3 = fma(Ji[j + 3], m.d[j + 3], acc3);
+            acc0 = fma(Ji[k], m.d[k], acc0);
+            acc1 = fma(Ji[k + 1], m.d[k + 1], acc1);
           }
-          for (; j < NW; j++) acc0 = fma(Ji[j], m.d[j], acc0);
+          if (k < q) acc0 = fma(Ji[k], m.d[k], acc0);
         }
-        z[s] = -((acc0 + acc1) + (acc2 + acc3));
+        z[s] = acc0 + acc1;
+        zzp = fma(z[s], z[s], zzp);
+      }
+      // re-orthogonalise once when most of g lies in span(J1) (the subtraction above lost digits): "twice is enough"
+      double zz = warp_sum(zzp);
+      {
+        if (q > 0 && zz < 0.01 * gg && zz > fmax(FQ_EPS_DEP * gg, FQ_ZZ_FLOOR))
+        {
+          __syncwarp();
+#pragma unroll
+          for (int s = 0; s < SLOTS; s++)
+          {
+            const int i = lane + 32 * s;
+            if (i < NW) m.zb[i] = z[s];
+          }
+          __syncwarp();
+          double c[SLOTS];
+#pragma unroll
+          for (int s = 0; s < SLOTS; s++)
+          {
+            const int k = lane + 32 * s;
+            c[s] = 0;
+            if (k < q)
+            {
+              for (int i = 0; i < NW; i++) c[s] = fma(m.J[i * LD + k], m.zb[i], c[s]);
+              dreg[s] -= c[s];                       // g = J1 (d1 - c) - z': the new R column stays consistent
+              m.d[k] = c[s];
+            }
+          }
+          __syncwarp();
+          zzp = 0;
+#pragma unroll
+          for (int s = 0; s < SLOTS; s++)
+          {
+            const int i = lane + 32 * s;
+            if (i < NW)
+            {
+              const double* Ji = m.J + i * LD;
+              double acc = z[s];
+              for (int k = 0; k < q; k++) acc = fma(-Ji[k], m.d[k], acc);
+              z[s] = acc;
+            }
+            zzp = fma(z[s], z[s], zzp);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int s = 0; s < SLOTS; s++)
+          {
+            const int k = lane + 32 * s;
+            if (k < q) m.d[k] = dreg[s];
+          }
+          zz = warp_sum(zzp);
+        }
       }
       // ---- r = R^-1 d1 (registers + shuffles)
 #pragma unroll
@@ -437,8 +495,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
           else if (j == k) r[s] = rk;
         }
       }
-      // ---- dual ratio test, |d2|^2 and the step scalars in one straight-line block: the two shuffle trees and the
-      //      MUFU seeds are independent, so their latencies overlap
+      // ---- dual ratio test and the step scalars
       double best = INFINITY;
       int bk = -1;
 #pragma unroll
@@ -451,13 +508,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
           if (ratio < best) { best = ratio; bk = k; }
         }
       }
-      double zz = zzp, t1 = best;
-#pragma unroll
-      for (int o = 16; o; o >>= 1)
-      {
-        zz += __shfl_xor_sync(FULL, zz, o);
-        t1 = fmin(t1, __shfl_xor_sync(FULL, t1, o));
-      }
+      const double t1 = warp_min(best);
       const double zzs = fmax(zz, 1e-300);
       const double rn = fast_rsqrt(zzs), rzz = fast_rcp(zzs);
       const bool dep = zz <= fmax(FQ_EPS_DEP * gg, FQ_ZZ_FLOOR);
@@ -470,10 +521,8 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
       const double t2 = dep ? INFINITY : viol * rzz;
       if (t1 == INFINITY && t2 == INFINITY) { status = 0; break; }
       if (t2 <= t1)
-      { // ---- full step: the row becomes active
+      { // ---- full step: the row becomes active; new basis vector = normalised residual of g
         const double nrm = zz * rn;
-        const double dq = m.d[q], sgn = dq >= 0 ? 1.0 : -1.0;
-        const double beta = fast_rcp(fma(fabs(dq), nrm, zz)), vq = fma(sgn, nrm, dq);
 #pragma unroll
         for (int s = 0; s < SLOTS; s++)
         {
@@ -481,14 +530,10 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
           if (i < NW)
           {
             m.w[i] = fma(t2, z[s], m.w[i]);
-            double* Ji = m.J + i * LD;
-            const double bu = beta * fma(sgn * nrm, Ji[q], -z[s]);
-            Ji[q] = fma(-bu, vq, Ji[q]);
-#pragma unroll 4
-            for (int j = q + 1; j < NW; j++) Ji[j] = fma(-bu, m.d[j], Ji[j]);
+            m.J[i * LD + q] = -z[s] * rn;
           }
           if (i < q) { lam[s] = fma(-t2, r[s], lam[s]); m.R[q * LD + i] = dreg[s]; }
-          if (i == q) { lam[s] = lam_p + t2; rdinv[s] = -sgn * rn; m.R[q * LD + q] = -sgn * nrm; }
+          if (i == q) { lam[s] = lam_p + t2; rdinv[s] = rn; m.R[q * LD + q] = nrm; }
         }
         q++;
         __syncwarp();
@@ -570,14 +615,12 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
     }
     total_rows = build_items<D>(m, sfo, seg_ofs, lane, N, p);
   }
-  // ---- J = I, w = 0
-  for (int idx = lane; idx < NW * LD; idx += 32) m.J[idx] = 0.0;
-  __syncwarp();
+  // ---- w = 0 (the thin factor J1 starts empty: nothing to initialise)
 #pragma unroll
   for (int s = 0; s < SLOTS; s++)
   {
     const int j = lane + 32 * s;
-    if (j < NW) { m.J[j * LD + j] = 1.0; m.w[j] = 0.0; }
+    if (j < NW) m.w[j] = 0.0;
   }
   __syncwarp();
 
@@ -668,6 +711,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <
     m.Y = p;   p += 3 * D::NYP;
     m.w = p;   p += D::NW;
     m.d = p;   p += D::NW + 2;
+    m.zb = p;  p += D::NW;
     m.items = reinterpret_cast<unsigned short*>(p);
     seg_ofs = sfo + 40 + warp * 32;
   }

@@ -10,9 +10,11 @@ ZZ_FLOOR = 1e-30
 MAX_ITERS = 400
 
 
-def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised=False):
+def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised=False, thin=False):
     """-> (status, cost, coeffs[N,12], iters).  normalised=False mirrors the size-generic kernel (entering row = largest
-    violation); normalised=True mirrors the size-specialised kernel (largest (violation - tol) / |TZ[y]|)."""
+    violation); normalised=True mirrors the size-specialised kernel (largest (violation - tol) / |TZ[y]|).
+    thin=True: the thin factorisation of the specialised kernel (J1 = orthonormal basis of the active normals only,
+    Gram-Schmidt with one re-orthogonalisation pass when the residual is small) instead of the full orthogonal J."""
     TZ, T0, FT = tables
     ne = 3 if force_final else 2
     nz, NY = N - ne, 6 * N + 1
@@ -27,7 +29,7 @@ def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised
         rhs = np.array(tgt) - FT @ s0
         Yeq[ax] = T0[:, :3] @ s0 + T0[:, 3:] @ rhs
     w = np.zeros(nw)
-    J = np.eye(nw)
+    J = np.zeros((nw, nw)) if thin else np.eye(nw)
     R = np.zeros((nw, nw))
     lam = np.zeros(nw)
     q = 0
@@ -81,8 +83,18 @@ def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised
                 break
             viol = wv @ Y[:, y] - h
             d = J.T @ g
-            zz = d[q:] @ d[q:]
-            z = -J[:, q:] @ d[q:]
+            if thin:
+                d[q:] = 0.0
+                z = -(g - J[:, :q] @ d[:q])
+                zz = z @ z
+                if zz < 0.01 * gg and q > 0:                       # re-orthogonalise once ("twice is enough")
+                    c = J[:, :q].T @ z
+                    z = z - J[:, :q] @ c
+                    d[:q] = d[:q] - c                              # g = J1 (d1 - c) + (-z): keep the R column consistent
+                    zz = z @ z
+            else:
+                zz = d[q:] @ d[q:]
+                z = -J[:, q:] @ d[q:]
             r = np.linalg.solve(np.triu(R[:q, :q]), d[:q]) if q > 0 else np.zeros(0)
             dep = zz <= max(EPS_DEP * gg, ZZ_FLOOR)
             t1, l = np.inf, -1
@@ -97,15 +109,21 @@ def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised
                 w = w + t2 * z
                 lam[:q] -= t2 * r
                 lam_p += t2
-                dq, nrm = d[q], np.sqrt(zz)
-                sgn = 1.0 if dq >= 0 else -1.0
-                beta = 1.0 / (zz + abs(dq) * nrm)
-                v = d[q:].copy()
-                v[0] += sgn * nrm
-                u = -z + sgn * nrm * J[:, q]
-                J[:, q:] -= beta * np.outer(u, v)
-                R[:q, q] = d[:q]
-                R[q, q] = -sgn * nrm
+                nrm = np.sqrt(zz)
+                if thin:
+                    J[:, q] = -z / nrm                            # new basis vector: the normalised residual of g
+                    R[:q, q] = d[:q]
+                    R[q, q] = nrm
+                else:
+                    dq = d[q]
+                    sgn = 1.0 if dq >= 0 else -1.0
+                    beta = 1.0 / (zz + abs(dq) * nrm)
+                    v = d[q:].copy()
+                    v[0] += sgn * nrm
+                    u = -z + sgn * nrm * J[:, q]
+                    J[:, q:] -= beta * np.outer(u, v)
+                    R[:q, q] = d[:q]
+                    R[q, q] = -sgn * nrm
                 lam[q] = lam_p
                 q += 1
                 Y = Yof(w)

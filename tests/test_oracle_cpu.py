@@ -207,8 +207,9 @@ def test_kernel_mathematics_mirror_vs_oracle(oracle, N, P, ff):
             for s in sig_all[rng.choice(len(sig_all), min(3, len(sig_all)), replace=False)]:
                 dt = f * max(dti, 0.02)
                 rc, c, co, _ = oracle.solve_fixed(N, pb["x0"], pb["xf"], pb["lim"], dt, polys, s, ff)
-                for normalised in (False, True):
-                    st, cm, com, _ = km.solve(tab, N, pb["x0"], pb["xf"], pb["lim"], dt, polys, s, ff, normalised)
+                for normalised, thin in ((False, False), (True, False), (True, True)):
+                    # generic kernel / specialised pivot rule / specialised kernel's thin Gram-Schmidt factorisation
+                    st, cm, com, _ = km.solve(tab, N, pb["x0"], pb["xf"], pb["lim"], dt, polys, s, ff, normalised, thin)
                     assert (rc == 1) == (st == 1)
                     if rc == 1:
                         assert abs(c - cm) <= 1e-8 * max(1.0, c) and np.abs(co - com).max() <= 1e-7 * max(1.0, np.abs(co).max())
