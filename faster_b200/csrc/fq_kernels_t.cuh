@@ -761,13 +761,17 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <
       for (int i = threadIdx.x; i <= P && i < 36; i += blockDim.x) sfo[i] = a.face_ofs[p0 + i] - f0;
       rows_bad = __syncthreads_or(bad) != 0;       // also the barrier that publishes the staged rows
     }
-    for (;;)
+    // claim candidates one ahead: the global atomic for the NEXT candidate is issued before the current one is solved,
+    // so its round trip (~1 us) hides behind the solve instead of idling the warp between candidates
+    int c = 0;
+    if (lane == 0) c = atomicAdd(counters + prob, 1);
+    c = __shfl_sync(FULL, c, 0);
+    while (c < count)
     {
-      int c = 0;
-      if (lane == 0) c = atomicAdd(counters + prob, 1);
-      c = __shfl_sync(FULL, c, 0);
-      if (c >= count) break;
+      int cn = 0;
+      if (lane == 0) cn = atomicAdd(counters + prob, 1);
       solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, c_begin + c, lane, rows_bad);
+      c = __shfl_sync(FULL, cn, 0);
     }
     __syncthreads();                               // everyone is done with the staged rows
   }
