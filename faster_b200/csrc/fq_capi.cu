@@ -642,32 +642,23 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
   int max_pf = 0;
   for (int p = 0; p < P; p++) max_pf = std::max(max_pf, face_ofs[p + 1] - face_ofs[p]);
   const size_t nb = fq_bnb_node_bytes(N, force_final);
-  // ---- 1. non-decreasing assignments for every time allocation (the ordinary batch solve)
+  // ---- 1. non-decreasing assignments for every time allocation: the ordinary sweep (one launch + selection).  Its winner
+  //         is the first monotone-feasible time allocation `fstar` with that allocation's best monotone cost; earlier
+  //         allocations have no feasible monotone assignment, later ones cannot win.
   const long n_mono = fq_monotone_sigmas(N, P, nullptr, 0);
   if (n_mono <= 0 || n_mono > (1L << 20)) return fail(ctx, FQ_E_ARG, "assignment list too long");
   std::vector<uint8_t> mono((size_t)n_mono * N);
   fq_monotone_sigmas(N, P, mono.data(), n_mono);
-  const size_t n_cand = (size_t)n_dt * n_mono;
-  std::vector<double> gdt(n_cand), gcost(n_cand);
-  std::vector<uint8_t> gsig(n_cand * N), gfeas(n_cand);
-  for (int d = 0; d < n_dt; d++)
-    for (long k = 0; k < n_mono; k++)
-    {
-      gdt[(size_t)d * n_mono + k] = dts[d];
-      std::memcpy(&gsig[((size_t)d * n_mono + k) * N], &mono[(size_t)k * N], N);
-    }
-  int rc = fq_solve_batch(ctx, N, force_final, x0, xf, lim, P, face_ofs, Ab, (int)n_cand, gdt.data(), gsig.data(), gfeas.data(),
-                          gcost.data(), nullptr, nullptr);
-  if (rc) return rc;
+  int m_dt = -1, m_sig = -1;
+  double m_cost = INFINITY;
+  std::vector<double> m_coeffs((size_t)12 * N, 0.0);
+  int rc = gen_new_traj_impl(ctx, N, force_final, x0, xf, lim, P, face_ofs, Ab, n_dt, dts, (int)n_mono, mono.data(), &m_dt, &m_sig,
+                             &m_cost, m_coeffs.data(), 0.0, 0, nullptr, nullptr);
+  if (rc < 0) return rc;
+  const int fstar = rc == 1 ? m_dt : -1;
   std::vector<double> best(n_dt, INFINITY);
   std::vector<long> best_k(n_dt, -1);
-  int fstar = -1;
-  for (int d = 0; d < n_dt; d++)
-  {
-    for (long k = 0; k < n_mono; k++)
-      if (gfeas[(size_t)d * n_mono + k] && gcost[(size_t)d * n_mono + k] < best[d]) { best[d] = gcost[(size_t)d * n_mono + k]; best_k[d] = k; }
-    if (fstar < 0 && best_k[d] >= 0) fstar = d;
-  }
+  if (fstar >= 0) { best[fstar] = m_cost; best_k[fstar] = m_sig; }
   const int n_search = fstar >= 0 ? fstar + 1 : n_dt;       // later time allocations cannot win
   bool exact = nb != 0 && n_face <= 2047;
   std::vector<uint8_t> win_sigma(N, 0);
@@ -811,7 +802,13 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
   if (dt_index) *dt_index = win_dt;
   if (win_dt < 0) { if (cost) *cost = INFINITY; return 0; }
   if (sigma_out) std::memcpy(sigma_out, win_sigma.data(), N);
-  // ---- 3. coefficients of the winner: one ordinary fixed-assignment solve
+  // ---- 3. coefficients of the winner: the monotone sweep already has them unless the tree found something better
+  if (win_dt == fstar && fstar >= 0 && std::memcmp(win_sigma.data(), &mono[(size_t)best_k[fstar] * N], N) == 0)
+  {
+    if (cost) *cost = m_cost;
+    if (coeffs) std::memcpy(coeffs, m_coeffs.data(), sizeof(double) * 12 * (size_t)N);
+    return 1;
+  }
   uint8_t f1 = 0;
   double c1 = INFINITY;
   std::vector<double> co((size_t)12 * N);

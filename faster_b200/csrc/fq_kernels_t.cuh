@@ -572,7 +572,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
                                 const int* __restrict__ sfo, const WarpState<D>& m, int* __restrict__ seg_ofs,
                                 int prob, int cand, int lane, bool rows_bad)
 {
-  constexpr int N = D::N, NW = D::NW, NYP = D::NYP, LD = D::LD, SLOTS = D::SLOTS;
+  constexpr int N = D::N, NW = D::NW, NYP = D::NYP, SLOTS = D::SLOTS;
   const double dt = a.dt[cand];
   const double inv1 = 1.0 / dt, inv2 = inv1 * inv1, inv3 = inv2 * inv1;
   const double lim0 = a.lim[prob * 3 + 0], lim1 = a.lim[prob * 3 + 1], lim2 = a.lim[prob * 3 + 2];

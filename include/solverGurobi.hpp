@@ -84,7 +84,7 @@ public:
   //   MONOTONE  the non-decreasing ones only, C(N+P-1, P-1) (identical genNewTraj results in 960/960 measured sweeps,
   //             see DESIGN.md section 2);
   //   EXACT     branch-and-bound over all P^N on the GPU (fq_gen_new_traj_exact): the exact MIQP optimum for any size,
-  //             ~160 us per sweep instead of ~80;
+  //             ~125 us per sweep instead of ~80;
   //   AUTO      (default) ALL while P^N <= auto_all_limit (4096: covers the shipped yaml, N=6 and <=3 polytopes: 729),
   //             EXACT beyond -- i.e. always the reference's MIQP optimum.
   void setAssignmentMode(AssignmentMode m, long max_assignments = 16384, long auto_all_limit = 4096)
