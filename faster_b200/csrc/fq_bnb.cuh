@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
 #pragma unroll
     for (int t = 1; t < 16; t++)
       if (lane == t && t <= k) p = sig[t];
-    total_rows = build_items<D>(m, sfo, seg_ofs, lane, k + 1, p);
+    total_rows = build_items<D>(m, sfo, seg_ofs, lane, k + 1, p, a.item_cap);
+    if (total_rows < 0) { if (lane == 0) b.flags[0] = 1; return; }
   }
   int it = 0, bkey = 0;
   unsigned bcode = 0;

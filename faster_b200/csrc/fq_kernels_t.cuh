@@ -260,7 +260,7 @@ __device__ __forceinline__ void setup_rows(const FqKernelArgs& a, int prob, doub
 // `p` = polytope of segment `lane` (meaningful for lane < n_seg).  Returns the number of items.
 template <class D>
 __device__ __forceinline__ int build_items(const WarpState<D>& m, const int* __restrict__ sfo, int* __restrict__ seg_ofs,
-                                           int lane, int n_seg, int p)
+                                           int lane, int n_seg, int p, int item_cap)
 {
   int F = 0;
   if (lane < n_seg) F = sfo[p + 1] - sfo[p];
@@ -274,6 +274,7 @@ __device__ __forceinline__ int build_items(const WarpState<D>& m, const int* __r
     if (lane >= o) incl += v;
   }
   const int total_rows = __shfl_sync(FULL, incl, n_seg - 1);
+  if (total_rows > item_cap) return -1;     // a wrong max_faces_per_polytope hint (device-pointer entry): refuse, never overrun
   // seg_ofs[t] = first item of segment t; seg_ofs[16 + t] = (need_cp0 << 11) | first staged face of sigma[t]
   if (lane < n_seg) { seg_ofs[lane] = incl - F; seg_ofs[16 + lane] = (need0 << 11) | sfo[p]; }
   else if (lane < 16) seg_ofs[lane] = 0x7fffffff;
@@ -613,7 +614,19 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
       p = a.sigma[(size_t)cand * N + lane];
       if (p >= P) p = P - 1;
     }
-    total_rows = build_items<D>(m, sfo, seg_ofs, lane, N, p);
+    total_rows = build_items<D>(m, sfo, seg_ofs, lane, N, p, a.item_cap);
+    if (total_rows < 0)
+    { // the row list does not fit: report "not solved" (iters = -2 marks the cause)
+      if (lane == 0)
+      {
+        a.feasible[cand] = 0;
+        a.cost[cand] = INFINITY;
+        if (a.iters) a.iters[cand] = -2;
+      }
+      if (a.coeffs)
+        for (int idx = lane; idx < 12 * N; idx += 32) a.coeffs[(size_t)cand * N * 12 + idx] = 0.0;
+      return;
+    }
   }
   // ---- w = 0 (the thin factor J1 starts empty: nothing to initialise)
 #pragma unroll

@@ -575,3 +575,30 @@ def test_full_host_pipeline_then_gpu_solve(solver, oracle):
             assert d > 0.3
             n += 1
     assert n >= 5
+
+
+def test_wrong_polytope_size_hint_is_refused_not_overrun(solver):
+    """The device-pointer entry trusts the caller's "max_faces_per_polytope" hint to size the per-warp row list; a hint
+    that is too small must make the affected candidates "not solved" (iters = -2), never write past the list."""
+    import torch
+    pb = cr.make_corridor(41, 3, 10)
+    sig = cr.monotone_sigmas(10, 3)[:16]
+    P, fo, Ab = capi.pack_polys(pb["polys"])
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = dict(x0=t(pb["x0"]), xf=t(pb["xf"]), lim=t(pb["lim"]), po=t(np.array([0, P], np.int32)), fo=t(fo), Ab=t(Ab),
+             co=t(np.array([0, 16], np.int32)), dt=t(np.full(16, 0.6)), sg=t(sig))
+    res = {}
+    for hint in (2, int(np.diff(fo).max())):
+        solver.set_option("max_faces_per_polytope", hint)
+        feas = torch.ones(16, dtype=torch.uint8, device=dev)
+        cost = torch.zeros(16, dtype=torch.float64, device=dev)
+        iters = torch.zeros(16, dtype=torch.int32, device=dev)
+        solver.solve_multi_dev(10, True, 1, d["x0"].data_ptr(), d["xf"].data_ptr(), d["lim"].data_ptr(), d["po"].data_ptr(),
+                               d["fo"].data_ptr(), d["Ab"].data_ptr(), d["co"].data_ptr(), 16, int(fo[-1]), d["dt"].data_ptr(),
+                               d["sg"].data_ptr(), feas.data_ptr(), cost.data_ptr(), 0, iters.data_ptr())
+        torch.cuda.synchronize()
+        res[hint] = (feas.cpu().numpy(), iters.cpu().numpy())
+    solver.set_option("max_faces_per_polytope", 0)
+    assert not res[2][0].any() and (res[2][1] == -2).all()
+    assert res[int(np.diff(fo).max())][0].any()
