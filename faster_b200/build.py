@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfaster_b200.so")
 SOURCES = ["fq_kernels.cu", "fq_capi.cu", "fq_host.cpp", "fq_decomp.cpp", "fq_jps.cpp"]
-HEADERS = ["fq_kernels.cuh", "fq_plan.h", os.path.join("..", "..", "include", "faster_b200.h")]
+PUBLIC_HEADER = os.path.join(HERE, "..", "include", "faster_b200.h")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-cudart", "static"]
 
@@ -20,8 +20,8 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS) or \
-        os.path.getmtime(os.path.abspath(__file__)) > t
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [PUBLIC_HEADER, os.path.abspath(__file__)]
+    return any(os.path.getmtime(f) > t for f in deps)      # every file of csrc/ (sources and all .cuh/.h)
 
 
 def build(force=False, verbose=False, extra_flags=(), out=None):
