@@ -159,6 +159,9 @@ def main():
     ap.add_argument("--ref-corridors", type=int, default=16, help="corridors per step of the CPU arm (bounded sample)")
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-blocking", action="store_true", help="e2e leg: blocking fq_solve_multi calls, one after the other")
+    ap.add_argument("--slices", type=int, default=0, help="throughput_slices option for the e2e leg (0 = library default)")
+    ap.add_argument("--single-stream", action="store_true", help="whole and safe launch of a step on one stream (serialised)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -204,21 +207,45 @@ def main():
     # hint for the device-pointer API (the host-pointer API derives it itself): sizes the per-warp row list
     solver.set_option("max_faces_per_polytope", max(w["max_poly_faces"] for w in works))
 
+    # the whole and the safe launch of a step are independent (different inputs and outputs), so the safe one goes on
+    # a second stream forked from / joined back into the timing stream: its CTAs start on the SMs the whole launch's
+    # persistent CTAs vacate, instead of waiting for the last one to finish
+    tstream2 = torch.cuda.Stream(device=dev)
+    streams = [stream, tstream2.cuda_stream] if not args.single_stream else [stream, stream]
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+
     def step_resident(with_iters=False):
-        for w, d, o in zip(works, devt, outs_d):
+        if not args.single_stream:
+            ev_fork.record(tstream)
+            tstream2.wait_event(ev_fork)
+        for w, d, o, st in zip(works, devt, outs_d, streams):
             solver.solve_multi_dev(w["N"], w["ff"], w["n_prob"], d["x0"].data_ptr(), d["xf"].data_ptr(),
                                    d["lim"].data_ptr(), d["poly_ofs"].data_ptr(), d["face_ofs"].data_ptr(),
                                    d["Ab"].data_ptr(), d["cand_ofs"].data_ptr(), CAND, w["max_faces"],
                                    d["dt"].data_ptr(), d["sigma"].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), 0,
-                                   o[2].data_ptr() if with_iters else 0, stream)
+                                   o[2].data_ptr() if with_iters else 0, st)
+        if not args.single_stream:
+            ev_join.record(tstream2)
+            tstream.wait_event(ev_join)
         if world > 1:   # the path's one exchange: all-gather of the per-candidate costs (+inf = infeasible)
             shard.all_gather_costs(cost_all, world * C, 2 * CAND)
 
+    # e2e: host buffers through the C ABI, one solver context per trajectory kind (the reference keeps two solver
+    # objects, sg_whole_ and sg_safe_).  Each batch is enqueued without waiting (fq_solve_multi_async), then both are
+    # waited for: the safe batch uploads and starts while the whole batch's last launch drains.
+    solvers_e2e = [solver, capi.Solver(local)]
+    if args.slices:
+        for sv in solvers_e2e:
+            sv.set_option("throughput_slices", args.slices)
+    e2e_np = [tuple(h[k].numpy() for k in ("x0", "xf", "lim", "poly_ofs", "face_ofs", "Ab", "cand_ofs", "dt", "sigma")) for h in host]
+    e2e_out = [(o[0].numpy(), o[1].numpy(), None, None) for o in outs_h]
+
     def step_e2e():
-        for w, h, o in zip(works, host, outs_h):
-            solver.solve_multi(w["N"], w["ff"], h["x0"].numpy(), h["xf"].numpy(), h["lim"].numpy(),
-                               h["poly_ofs"].numpy(), h["face_ofs"].numpy(), h["Ab"].numpy(), h["cand_ofs"].numpy(),
-                               h["dt"].numpy(), h["sigma"].numpy(), out=(o[0].numpy(), o[1].numpy(), None, None))
+        for sv, w, a, o in zip(solvers_e2e, works, e2e_np, e2e_out):
+            sv.solve_multi(w["N"], w["ff"], *a, out=o, deferred=not args.e2e_blocking)
+        if not args.e2e_blocking:
+            for sv in solvers_e2e:
+                sv.wait()
 
     def barrier():
         if world > 1:
@@ -382,10 +409,13 @@ def main():
                 "config": {"workload": "cfg2-pairs: N=10, whole P=3 + safe P=4, 1024 pairs/corridor (16 dt x 64 sigma)",
                            "corridors_per_gpu": C, "pairs_per_step": pairs_per_step,
                            "l2": "flushed between timed steps (256 MiB memset outside the per-step events)",
+                           "streams": "one (whole then safe)" if args.single_stream else "two (safe launch forked from / joined into the timed stream)",
                            "parallelism": "corridor shards per rank, all-gather of costs" if world > 1 else "single GPU",
                            "feasible_fraction": feas_frac, "mean_active_set_iters": float(iters.mean()),
                            "e2e_matches_resident": same},
-                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "how": "fq_solve_multi, blocking, whole then safe" if args.e2e_blocking else
+                               "fq_solve_multi_async on two solver contexts (whole, safe) + fq_wait; pinned host buffers"},
                 "gpu_launches": 2 * args.steps,
                 "replan_pipeline_us": pipeline,
                 "replan_latency_us": {"value": replan_us, "what": "fq_gen_new_traj: 10 factors x 66 assignments, N=10, P=3, host in/out, median of 50",

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("FQ_LIB") or os.path.join(_HERE, "lib", "libfaster_b20
 _lib = None
 
 EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_set_option", "fq_solve_batch", "fq_solve_multi",
-           "fq_solve_multi_dev", "fq_gen_new_traj", "fq_gen_new_traj_sampled", "fq_gen_new_traj_exact", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
+           "fq_solve_multi_async", "fq_wait", "fq_solve_multi_dev", "fq_gen_new_traj", "fq_gen_new_traj_sampled", "fq_gen_new_traj_exact", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
            "fq_monotone_sigmas", "fq_plan_tables", "fq_ellipsoid_decomp", "fq_jps3d_plan", "fq_jps3d_plan_world", "fq_jps3d_rules"]
 
 
@@ -46,6 +46,8 @@ def lib():
         L.fq_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.fq_solve_multi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 13
+        L.fq_solve_multi_async.argtypes = L.fq_solve_multi.argtypes
+        L.fq_wait.argtypes = [C.c_void_p]
         L.fq_solve_multi_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7 + \
                                         [C.c_int, C.c_int] + [C.c_void_p] * 7
         L.fq_gen_new_traj.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + \
@@ -224,8 +226,9 @@ class Solver:
         return feas, cost, co, it
 
     def solve_multi(self, N, force_final, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dts, sigmas,
-                    want_coeffs=False, want_iters=False, out=None):
-        """Arrays as in fq_solve_multi; numpy (possibly pinned torch-backed) host arrays."""
+                    want_coeffs=False, want_iters=False, out=None, deferred=False):
+        """Arrays as in fq_solve_multi; numpy (possibly pinned torch-backed) host arrays.  deferred=True uses
+        fq_solve_multi_async: the outputs are valid after wait() (keep every array alive until then)."""
         n_prob = len(cand_ofs) - 1
         n = int(cand_ofs[-1])
         if out is None:
@@ -235,13 +238,18 @@ class Solver:
             it = np.zeros(n, np.int32) if want_iters else None
         else:
             feas, cost, co, it = out
-        self._check(self._L.fq_solve_multi(self._h, int(N), int(bool(force_final)), n_prob, x0.ctypes.data,
-                                           xf.ctypes.data, lim.ctypes.data, poly_ofs.ctypes.data, face_ofs.ctypes.data,
-                                           Ab.ctypes.data, cand_ofs.ctypes.data, dts.ctypes.data, sigmas.ctypes.data,
-                                           feas.ctypes.data, cost.ctypes.data,
-                                           co.ctypes.data if co is not None else None,
-                                           it.ctypes.data if it is not None else None))
+        fn = self._L.fq_solve_multi_async if deferred else self._L.fq_solve_multi
+        self._check(fn(self._h, int(N), int(bool(force_final)), n_prob, x0.ctypes.data,
+                       xf.ctypes.data, lim.ctypes.data, poly_ofs.ctypes.data, face_ofs.ctypes.data,
+                       Ab.ctypes.data, cand_ofs.ctypes.data, dts.ctypes.data, sigmas.ctypes.data,
+                       feas.ctypes.data, cost.ctypes.data,
+                       co.ctypes.data if co is not None else None,
+                       it.ctypes.data if it is not None else None))
         return feas, cost, co, it
+
+    def wait(self):
+        """fq_wait: drain everything enqueued on the context's own streams (deferred batches included)."""
+        self._check(self._L.fq_wait(self._h))
 
     def solve_multi_dev(self, N, force_final, n_prob, d_x0, d_xf, d_lim, d_poly_ofs, d_face_ofs, d_Ab, d_cand_ofs,
                         max_cand, max_faces, d_dt, d_sigma, d_feas, d_cost, d_coeffs=0, d_iters=0, stream=0):

@@ -71,6 +71,8 @@ struct fq_ctx
   int* d_counters = nullptr;      // ring of per-problem claim counters (one slot per launch in flight)
   int counters_cap = 0;           // problems per slot
   unsigned counters_pos = 0;
+  bool pending = false;           // a deferred fq_solve_multi_async is still using the arenas (settled by the next call / fq_wait)
+  int throughput_slices = 0;      // option "throughput_slices": launches a large host batch is cut into (0 = default 4)
   int max_poly_faces_hint = 0;    // option "max_faces_per_polytope" (device-pointer API only)
 };
 static const int kCounterSlots = 64;
@@ -173,6 +175,7 @@ extern "C" int fq_set_option(fq_ctx* ctx, const char* key, int value)
 {
   if (!ctx || !key) return FQ_E_ARG;
   if (std::string(key) == "force_generic_kernel") { ctx->force_generic = value != 0; return 0; }
+  if (std::string(key) == "throughput_slices") { ctx->throughput_slices = value > 0 && value <= 64 ? value : 0; return 0; }
   if (std::string(key) == "max_faces_per_polytope") { ctx->max_poly_faces_hint = value > 0 ? value : 0; return 0; }
   return fail(ctx, FQ_E_ARG, std::string("unknown option ") + key);
 }
@@ -230,6 +233,20 @@ extern "C" int fq_solve_multi_dev(fq_ctx* ctx, int N, int force_final, int n_pro
                       max_cand_per_prob, max_faces_per_prob, ctx->max_poly_faces_hint, d_dt, d_sigma, d_feasible, d_cost,
                       d_coeffs, d_iters, stream ? (cudaStream_t)stream : ctx->stream);
 }
+
+namespace
+{
+// a deferred call owns the context's arenas until it has drained: every entry point that reuses them settles first
+int settle(fq_ctx* ctx)
+{
+  if (!ctx->pending) return 0;
+  ctx->pending = false;
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream2));
+  FQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+}  // namespace
 
 namespace
 {
@@ -310,12 +327,16 @@ struct Trace
 };
 }  // namespace
 
-extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf,
-                              const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
-                              const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible,
-                              double* cost, double* coeffs, int32_t* iters)
+namespace
+{
+// deferred: return once everything is enqueued (large batches only; small ones complete before returning either way)
+int solve_multi_impl(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf,
+                     const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
+                     const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible,
+                     double* cost, double* coeffs, int32_t* iters, bool deferred)
 {
   if (!ctx) return FQ_E_ARG;
+  if (int src = settle(ctx)) return src;
   Trace tr;
   if (!x0 || !xf || !lim || !poly_ofs || !face_ofs || !cand_ofs || !dt || !feasible || !cost)
     return fail(ctx, FQ_E_ARG, "NULL argument");
@@ -377,7 +398,10 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
     if (pack_head) FQ_CUDA(cudaMemcpyAsync(din, ctx->h_in.p, L.dt, cudaMemcpyHostToDevice, st));
     FQ_CUDA(cudaEventRecord(ctx->ev_head, st));
     FQ_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_head, 0));
-    const int n_slices = n_prob < 4 ? n_prob : 4;
+    // measured (bench.py, 64 corridors x 1024 candidates): 4 slices are best for a blocking call (copies hide behind the
+    // solves), 2 when another context's batch is in flight as well (fewer, deeper launches: shorter tails)
+    const int want_slices = ctx->throughput_slices > 0 ? ctx->throughput_slices : (deferred ? 2 : 4);
+    const int n_slices = n_prob < want_slices ? n_prob : want_slices;
     int p_lo = 0;
     for (int k = 0; k < n_slices; k++)
     {
@@ -418,6 +442,7 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
     tr.mark("enqueue");
     const char* why = values_ok();                 // overlaps with the GPU work enqueued above
     tr.mark("finite");
+    if (deferred && !why) { ctx->pending = true; return 0; }     // fq_wait() (or the next call) completes it
     FQ_CUDA(cudaStreamSynchronize(ctx->stream2));
     FQ_CUDA(cudaStreamSynchronize(st));
     tr.mark("wait");
@@ -455,6 +480,32 @@ extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, c
   }
   return 0;
 }
+}  // namespace
+
+extern "C" int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf,
+                              const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
+                              const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible,
+                              double* cost, double* coeffs, int32_t* iters)
+{
+  return solve_multi_impl(ctx, N, force_final, n_prob, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dt, sigma, feasible, cost,
+                          coeffs, iters, false);
+}
+
+extern "C" int fq_solve_multi_async(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf,
+                                    const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
+                                    const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible,
+                                    double* cost, double* coeffs, int32_t* iters)
+{
+  return solve_multi_impl(ctx, N, force_final, n_prob, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dt, sigma, feasible, cost,
+                          coeffs, iters, true);
+}
+
+extern "C" int fq_wait(fq_ctx* ctx)
+{
+  if (!ctx) return FQ_E_ARG;
+  ctx->pending = true;          // also drains device-pointer launches made on the context's own stream
+  return settle(ctx);
+}
 
 extern "C" int fq_solve_batch(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf,
                               const double* lim, int P, const int* face_ofs, const double* Ab, int n_cand,
@@ -476,6 +527,7 @@ int gen_new_traj_impl(fq_ctx* ctx, int N, int force_final, const double* x0, con
                       int max_samples, double* samples, int* n_samples)
 {
   if (!ctx) return FQ_E_ARG;
+  if (int src = settle(ctx)) return src;
   Trace tr;
   if (!x0 || !xf || !lim || !dts) return fail(ctx, FQ_E_ARG, "NULL argument");
   if (P < 0 || P > FQ_MAX_POLY || n_dt <= 0) return fail(ctx, FQ_E_ARG, "bad P or n_dt");
@@ -629,6 +681,7 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
                                      long* nodes_out, int* exact_out)
 {
   if (!ctx) return FQ_E_ARG;
+  if (int src = settle(ctx)) return src;
   if (!x0 || !xf || !lim || !dts || n_dt <= 0) return fail(ctx, FQ_E_ARG, "NULL argument or n_dt <= 0");
   if (P < 0 || P > FQ_MAX_POLY) return fail(ctx, FQ_E_ARG, "bad P");
   if (nodes_out) *nodes_out = 0;

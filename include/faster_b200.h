@@ -51,7 +51,9 @@ void fq_destroy(fq_ctx* ctx);
 const char* fq_last_error(const fq_ctx* ctx);   /* ctx may be NULL: last creation error */
 
 /* Tuning / testing knobs.  "force_generic_kernel" (0/1): use the size-generic kernel even where a size-specialised one
- * exists (the two are independent implementations of the same solve; tests run both).  Returns 0 or FQ_E_ARG. */
+ * exists (the two are independent implementations of the same solve; tests run both).  "throughput_slices" (1..64, 0 =
+ * default: 4, or 2 for fq_solve_multi_async): how many launches a large host batch is cut into (upload / solve / download of consecutive slices
+ * overlap on two streams).  "max_faces_per_polytope": see fq_solve_multi_dev.  Returns 0 or FQ_E_ARG. */
 int fq_set_option(fq_ctx* ctx, const char* key, int value);
 
 /* One corridor problem, n_cand candidates (dt[i], sigma[i*N .. i*N+N-1]); HOST pointers.
@@ -76,6 +78,20 @@ int fq_solve_multi(fq_ctx* ctx, int N, int force_final, int n_prob, const double
                    const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
                    const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible, double* cost,
                    double* coeffs, int32_t* iters);
+
+/* fq_solve_multi without the final wait: returns once the copies and launches are enqueued (large batches; small ones
+ * are simply complete on return).  Outputs are valid after fq_wait(ctx) -- or after the next call on the same context,
+ * which settles a deferred call before it reuses the context's device buffers.  Input and output arrays must stay
+ * alive and untouched until then; pinned (page-locked) arrays make the copies truly asynchronous.  Two contexts (the
+ * reference keeps two solver objects, sg_whole_ and sg_safe_: faster.hpp:74-75) can thus have their batches in flight
+ * together, the second batch's CTAs filling the SMs that the first one's last launch leaves idle. */
+int fq_solve_multi_async(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf,
+                         const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
+                         const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible, double* cost,
+                         double* coeffs, int32_t* iters);
+/* Blocks until everything enqueued on the context's own streams has finished (deferred host batches and
+ * fq_solve_multi_dev launches made with stream == NULL). */
+int fq_wait(fq_ctx* ctx);
 
 /* Same as fq_solve_multi with every array already resident in DEVICE memory of the context's GPU.  The library
  * cannot read device arrays on the host, so the caller also passes `max_cand_per_prob` (largest

@@ -387,6 +387,35 @@ def test_throughput_copy_path_matches_latency_path(solver):
         assert np.array_equal(f_big[a:b], f1) and np.array_equal(c_big[a:b], c1)
 
 
+def test_deferred_host_batches_on_two_contexts(solver):
+    """fq_solve_multi_async + fq_wait: two contexts (the reference's sg_whole_ / sg_safe_) keep a whole and a safe batch in
+    flight together; results are bit-identical to the blocking call, a following call on the same context settles the
+    deferred one first, and the slice count does not change any bit."""
+    import bench
+    second = capi.Solver(0)
+    works = [bench.make_workload(32, 4100, "whole"), bench.make_workload(32, 4200, "safe")]   # > 512 KB: throughput path
+    args = [(w["N"], w["ff"], w["x0"], w["xf"], w["lim"], w["poly_ofs"], w["face_ofs"], w["Ab"], w["cand_ofs"], w["dt"], w["sigma"])
+            for w in works]
+    ref = [solver.solve_multi(*a) for a in args]                              # blocking
+    outs = []
+    for sv, a in zip((solver, second), args):
+        outs.append(sv.solve_multi(*a, deferred=True))
+    solver.wait(); second.wait()
+    for r, o in zip(ref, outs):
+        assert np.array_equal(r[0], o[0]) and np.array_equal(r[1], o[1])
+    assert ref[0][0].any() and not ref[0][0].all()
+    # a second call on a context with a deferred batch in flight: the first batch's outputs must be complete afterwards
+    o1 = solver.solve_multi(*args[0], deferred=True)
+    pb = works[0]["probs"][0]
+    g = solver.gen_new_traj(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], np.arange(1, 11) * 0.3, cr.monotone_sigmas(10, 3), True)
+    assert np.array_equal(o1[0], ref[0][0]) and np.array_equal(o1[1], ref[0][1]) and g["dt_index"] >= -1
+    for n_slices in (1, 2, 7):
+        solver.set_option("throughput_slices", n_slices)
+        o = solver.solve_multi(*args[1])
+        assert np.array_equal(o[0], ref[1][0]) and np.array_equal(o[1], ref[1][1])
+    solver.set_option("throughput_slices", 0)
+
+
 def test_non_finite_inputs_are_rejected_or_survive(solver):
     """NaN / Inf / non-positive dt: the host-pointer entries refuse them; the device-pointer entry cannot look at the
     data, so the kernels must come back (numeric failure -> infeasible) instead of faulting."""
