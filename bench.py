@@ -412,6 +412,7 @@ def main():
                            "streams": "one (whole then safe)" if args.single_stream else "two (safe launch forked from / joined into the timed stream)",
                            "parallelism": "corridor shards per rank, all-gather of costs" if world > 1 else "single GPU",
                            "feasible_fraction": feas_frac, "mean_active_set_iters": float(iters.mean()),
+                           "active_set_iters_p99_max": [float(torch.quantile(iters[::16], 0.99)), float(iters.max())],
                            "e2e_matches_resident": same},
                 "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "how": "fq_solve_multi, blocking, whole then safe" if args.e2e_blocking else

@@ -783,7 +783,10 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <
     {
       int cn = 0;
       if (lane == 0) cn = atomicAdd(counters + prob, 1);
-      solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, c_begin + c, lane, rows_bad);
+      // claims run from the LAST candidate of the problem down: in a time-allocation sweep (dt-major candidate lists,
+      // increasing dt) the rare very long solves -- dozens of active-set changes against a mean of ~5 -- sit at the large
+      // dt end, and a long solve started last is a long tail for the whole launch
+      solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, c_begin + (count - 1 - c), lane, rows_bad);
       c = __shfl_sync(FULL, cn, 0);
     }
     __syncthreads();                               // everyone is done with the staged rows
