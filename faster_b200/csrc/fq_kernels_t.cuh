@@ -27,7 +27,6 @@ namespace fqt
 {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int W = FQ_WARPS_PER_CTA;
-constexpr int CHUNK = 32;          // candidates per CTA
 constexpr unsigned BOX_FLAG = 0x40000000u;
 
 template <int N_, bool WHOLE_>
