@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-blocking", action="store_true", help="e2e leg: blocking fq_solve_multi calls, one after the other")
     ap.add_argument("--slices", type=int, default=0, help="throughput_slices option for the e2e leg (0 = library default)")
+    ap.add_argument("--safe-first", action="store_true", help="enqueue the safe launch of a step before the whole launch")
     ap.add_argument("--single-stream", action="store_true", help="whole and safe launch of a step on one stream (serialised)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -218,7 +219,8 @@ def main():
         if not args.single_stream:
             ev_fork.record(tstream)
             tstream2.wait_event(ev_fork)
-        for w, d, o, st in zip(works, devt, outs_d, streams):
+        order = (1, 0) if args.safe_first else (0, 1)
+        for w, d, o, st in [(works[k], devt[k], outs_d[k], streams[k]) for k in order]:
             solver.solve_multi_dev(w["N"], w["ff"], w["n_prob"], d["x0"].data_ptr(), d["xf"].data_ptr(),
                                    d["lim"].data_ptr(), d["poly_ofs"].data_ptr(), d["face_ofs"].data_ptr(),
                                    d["Ab"].data_ptr(), d["cand_ofs"].data_ptr(), CAND, w["max_faces"],

@@ -7,6 +7,12 @@
 #ifndef FQ_MIN_CTAS_PER_SM
 #define FQ_MIN_CTAS_PER_SM 4
 #endif
+#ifndef FQ_MIN_CTAS_WHOLE
+#define FQ_MIN_CTAS_WHOLE 4   // whole-mode kernels for N <= 10; 5 (96 registers, 20 B of spills) measured -3.5 %
+#endif
+#ifndef FQ_BACKSUB_PRESCALED
+#define FQ_BACKSUB_PRESCALED 1   // measured +1.0 % (tools/ab.sh, same box); 0 keeps the division on the chain
+#endif
 #define FQ_EPS_DEP 1e-18      // squared sine below which a new normal counts as dependent on the active set
 #define FQ_ZZ_FLOOR 1e-30
 #define FQ_MAX_ITERS 400

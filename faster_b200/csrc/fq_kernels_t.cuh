@@ -480,6 +480,23 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
         }
       }
       // ---- r = R^-1 d1 (registers + shuffles)
+#if FQ_BACKSUB_PRESCALED
+      // every lane pre-divides its own row by the diagonal (R(j,k) / R(j,j) does not depend on r_k), so the chain from
+      // one r_k to the next is a shuffle and one FMA
+#pragma unroll
+      for (int s = 0; s < SLOTS; s++) r[s] = dreg[s] * rdinv[s];
+      for (int k = q - 1; k >= 0; k--)
+      {
+        const int ks = k >> 5;
+        const double rk = __shfl_sync(FULL, (SLOTS > 1 && ks == 1) ? r[SLOTS - 1] : r[0], k & 31);
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++)
+        {
+          const int j = lane + 32 * s;
+          if (j < k) r[s] = fma(-m.R[k * LD + j] * rdinv[s], rk, r[s]);
+        }
+      }
+#else
 #pragma unroll
       for (int s = 0; s < SLOTS; s++) r[s] = dreg[s];
       for (int k = q - 1; k >= 0; k--)
@@ -495,6 +512,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
           else if (j == k) r[s] = rk;
         }
       }
+#endif
       // ---- dual ratio test and the step scalars
       double best = INFINITY;
       int bk = -1;
@@ -686,7 +704,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
 // drained; several CTAs may drain the same problem.  Block-wide barriers happen only when a CTA changes problem, and
 // at the end of the launch every warp finishes within one candidate of the others.
 template <int N_, bool WHOLE_>
-__global__ void __launch_bounds__(W * 32, (N_ <= 10 ? FQ_MIN_CTAS_PER_SM : (N_ <= 15 ? 3 : 2)))
+__global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOLE : FQ_MIN_CTAS_PER_SM) : (N_ <= 15 ? 3 : 2)))
     fq_solve_kernel_t(const FqKernelArgs a, int* __restrict__ counters)
 {
   using D = Dims<N_, WHOLE_>;
