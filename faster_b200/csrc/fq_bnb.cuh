@@ -39,7 +39,7 @@ struct LeafRec
 };
 
 template <class D>
-__host__ __device__ constexpr int node_doubles() { return 2 * D::NW * D::LD + 3 * D::NW + (D::NW & 1); }
+__host__ __device__ constexpr int node_doubles() { return D::JR + 3 * D::NW + ((D::JR + 3 * D::NW) & 1); }
 template <class D>
 __host__ __device__ constexpr size_t node_bytes() { return sizeof(NodeHdr) + sizeof(double) * node_doubles<D>(); }
 
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
   {
     double* p = reinterpret_cast<double*>(wraw + (size_t)warp * pwb);
     m.J = p;   p += NW * LD;
-    m.R = p;   p += NW * LD;
+    m.R = p;   p += D::RSZ;
     m.Y = p;   p += 3 * NYP;
     m.w = p;   p += NW;
     m.d = p;   p += NW + 2;
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
   else
   {
     const double* st = reinterpret_cast<const double*>(pn + sizeof(NodeHdr));
-    for (int idx = lane; idx < 2 * NW * LD; idx += 32) m.J[idx] = st[idx];          // J then R (contiguous in both)
-    const double* v = st + 2 * NW * LD;
+    for (int idx = lane; idx < D::JR; idx += 32) m.J[idx] = st[idx];          // J then R (contiguous in both)
+    const double* v = st + D::JR;
 #pragma unroll
     for (int s = 0; s < SLOTS; s++)
     {
@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
     for (int t = 0; t < 16; t++) h->sigma[t] = t <= k ? sig[t] : 0;
   }
   double* st = reinterpret_cast<double*>(cn + sizeof(NodeHdr));
-  for (int idx = lane; idx < 2 * NW * LD; idx += 32) st[idx] = m.J[idx];
-  double* v = st + 2 * NW * LD;
+  for (int idx = lane; idx < D::JR; idx += 32) st[idx] = m.J[idx];
+  double* v = st + D::JR;
 #pragma unroll
   for (int s = 0; s < SLOTS; s++)
   {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
 template <int N_, bool WHOLE_>
 cudaError_t launch_level(const BnbArgs& b, cudaStream_t stream)
 {
-  const size_t smem = smem_bytes_t<N_, WHOLE_>(b.k.max_faces, b.k.item_cap);
+  const size_t smem = smem_bytes_t<N_, WHOLE_>(b.k.max_faces, b.k.item_cap, 1);   // one CTA-wide copy of the rows
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   auto kern = fq_bnb_level_kernel<N_, WHOLE_>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

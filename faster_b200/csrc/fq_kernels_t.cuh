@@ -42,7 +42,11 @@ struct Dims
   static constexpr int TZLD = NZ | 1;            // odd row stride of TZ in shared memory
   static constexpr int SLOTS = (NW + 31) / 32;   // elements of an NW-vector per lane
   static constexpr int RPL = (NY + 31) / 32;     // Y rows per lane
-  static constexpr int PER_WARP_DOUBLES = 2 * NW * LD + 3 * NYP + 3 * NW + 2;
+  static constexpr int RSZ = FQ_PACKED_R ? NW * (NW + 1) / 2 : NW * LD;   // doubles of the triangular factor
+  static constexpr int JR = NW * LD + RSZ;                                // J then R, contiguous
+  static constexpr int PER_WARP_DOUBLES = JR + 3 * NYP + 3 * NW + 2;
+  // element (row j, column k), j <= k, of R
+  __host__ __device__ static constexpr int ri(int j, int k) { return FQ_PACKED_R ? (k * (k + 1)) / 2 + j : k * LD + j; }
 };
 // per-warp bytes: solver state + item list (item_cap 16-bit entries)
 template <class D>
@@ -83,7 +87,7 @@ template <class D>
 struct WarpState
 {
   double* J;            // NW x LD row-major
-  double* R;            // column-major: R(j,k) at R[k*LD + j]
+  double* R;            // upper triangular, column-major: R(j,k) at R[D::ri(j,k)] (packed when FQ_PACKED_R)
   double* Y;            // 3 x NYP
   double* w;            // NW
   double* d;            // NW
@@ -150,6 +154,26 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
                                          double (&rdinv)[D::SLOTS])
 {
   constexpr int LD = D::LD;
+#if FQ_PACKED_R
+  // The columns right of l move one place left and become upper Hessenberg: the element below the new diagonal of
+  // column k is the OLD diagonal of column k+1.  Packed storage has no room for it, so each lane keeps the old diagonal
+  // of "its" column in a register; rotation j reads it by shuffle (no earlier rotation touches row j+1).
+  double dg[D::SLOTS];
+#pragma unroll
+  for (int s = 0; s < D::SLOTS; s++)
+  {
+    const int k = lane + 32 * s;
+    dg[s] = k < q ? m.R[D::ri(k, k)] : 0.0;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < D::SLOTS; s++)
+  {
+    const int j = lane + 32 * s;                 // this lane moves row j of every column that keeps a row j
+    if (j < q)
+      for (int k = (l > j ? l : j); k < q - 1; k++) m.R[D::ri(j, k)] = m.R[D::ri(j, k + 1)];
+  }
+#else
   // R: columns l+1..q-1 move left (each lane moves its own rows)
 #pragma unroll
   for (int s = 0; s < D::SLOTS; s++)
@@ -158,6 +182,7 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
     if (j < q)
       for (int k = l; k < q - 1; k++) m.R[k * LD + j] = m.R[(k + 1) * LD + j];
   }
+#endif
   // lam: element k <- element k+1 for k in [l, q-1)
   {
     double nxt[D::SLOTS];
@@ -178,7 +203,13 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
   __syncwarp();
   for (int j = l; j < q - 1; j++)
   {
+#if FQ_PACKED_R
+    const double p = m.R[D::ri(j, j)];
+    const int js = (j + 1) >> 5;
+    const double sb = __shfl_sync(FULL, (D::SLOTS > 1 && js == 1) ? dg[D::SLOTS - 1] : dg[0], (j + 1) & 31);
+#else
     const double p = m.R[j * LD + j], sb = m.R[j * LD + j + 1];
+#endif
     const double h2 = fma(p, p, sb * sb);
     double c = 1.0, sn = 0.0, hi = 0.0;
     if (h2 > 0) { hi = fast_rsqrt(h2); c = p * hi; sn = sb * hi; }
@@ -187,6 +218,15 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
     for (int s = 0; s < D::SLOTS; s++)
     {
       const int k = lane + 32 * s;
+#if FQ_PACKED_R
+      if (k > j && k < q - 1)
+      { // rows j, j+1 of R at column k (both inside the triangle)
+        const double u = m.R[D::ri(j, k)], v = m.R[D::ri(j + 1, k)];
+        m.R[D::ri(j, k)] = fma(c, u, sn * v);
+        m.R[D::ri(j + 1, k)] = fma(c, v, -sn * u);
+      }
+      if (k == j) { m.R[D::ri(j, j)] = fma(c, p, sn * sb); rdinv[s] = hi; }     // the element below it rotates to zero
+#else
       if (k >= j && k < q - 1)
       { // rows j, j+1 of R at column k
         const double u = m.R[k * LD + j], v = m.R[k * LD + j + 1];
@@ -194,6 +234,7 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
         m.R[k * LD + j + 1] = fma(c, v, -sn * u);
       }
       if (k == j) rdinv[s] = hi;                 // new diagonal is h = sqrt(h2)
+#endif
       if (k < D::NW)
       { // columns j, j+1 of J at row k
         const double u = m.J[k * LD + j], v = m.J[k * LD + j + 1];
@@ -493,7 +534,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
         for (int s = 0; s < SLOTS; s++)
         {
           const int j = lane + 32 * s;
-          if (j < k) r[s] = fma(-m.R[k * LD + j] * rdinv[s], rk, r[s]);
+          if (j < k) r[s] = fma(-m.R[D::ri(j, k)] * rdinv[s], rk, r[s]);
         }
       }
 #else
@@ -508,7 +549,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
         for (int s = 0; s < SLOTS; s++)
         {
           const int j = lane + 32 * s;
-          if (j < k) r[s] = fma(-m.R[k * LD + j], rk, r[s]);
+          if (j < k) r[s] = fma(-m.R[D::ri(j, k)], rk, r[s]);
           else if (j == k) r[s] = rk;
         }
       }
@@ -550,8 +591,8 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
             m.w[i] = fma(t2, z[s], m.w[i]);
             m.J[i * LD + q] = -z[s] * rn;
           }
-          if (i < q) { lam[s] = fma(-t2, r[s], lam[s]); m.R[q * LD + i] = dreg[s]; }
-          if (i == q) { lam[s] = lam_p + t2; rdinv[s] = rn; m.R[q * LD + q] = nrm; }
+          if (i < q) { lam[s] = fma(-t2, r[s], lam[s]); m.R[D::ri(i, q)] = dreg[s]; }
+          if (i == q) { lam[s] = lam_p + t2; rdinv[s] = rn; m.R[D::ri(q, q)] = nrm; }
         }
         q++;
         __syncwarp();
@@ -698,11 +739,13 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
   __syncwarp();
 }
 
-// Persistent CTAs.  counters[j] = next unclaimed candidate of problem j (zeroed before the launch).  A CTA adopts a
-// problem that still has unclaimed candidates (scanning from a CTA-specific start so CTAs spread over the problems),
-// stages its polytope rows once, and its warps claim candidates one by one with a global atomic until the problem is
-// drained; several CTAs may drain the same problem.  Block-wide barriers happen only when a CTA changes problem, and
-// at the end of the launch every warp finishes within one candidate of the others.
+// Persistent CTAs.  counters[j] = next unclaimed candidate of problem j (zeroed before the launch).  A CTA (or, with
+// FQ_WARP_ADOPT, every warp on its own) adopts a problem that still has unclaimed candidates (scanning from its own start
+// so the adopters spread over the problems), stages the problem's polytope rows once, and claims candidates one by one
+// with a global atomic until the problem is drained; several adopters may drain the same problem.
+//   FQ_WARP_ADOPT = 0: rows staged once per CTA; block-wide barriers when the CTA changes problem.
+//   FQ_WARP_ADOPT = 1: rows staged per warp (W copies); no barrier after the plan tables are staged, a warp never waits
+//                      for its CTA-mates' last solves.
 template <int N_, bool WHOLE_>
 __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOLE : FQ_MIN_CTAS_PER_SM) : (N_ <= 15 ? 3 : 2)))
     fq_solve_kernel_t(const FqKernelArgs a, int* __restrict__ counters)
@@ -710,14 +753,15 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
   using D = Dims<N_, WHOLE_>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_prob;
+  constexpr int SAB_COPIES = FQ_WARP_ADOPT ? W : 1;
 
   double* sm = reinterpret_cast<double*>(smem_raw);
-  double* sAb = sm;            sm += 4 * a.max_faces;
+  double* sAb0 = sm;           sm += SAB_COPIES * 4 * a.max_faces;
   double* TZ = sm;             sm += D::NY * D::TZLD;
   double* SY = sm;             sm += D::NY;
   unsigned char* wraw = reinterpret_cast<unsigned char*>(sm);
   const int pwb = per_warp_bytes<D>(a.item_cap);
-  int* sfo = reinterpret_cast<int*>(wraw + (size_t)W * pwb);
+  int* sfo0 = reinterpret_cast<int*>(wraw + (size_t)W * pwb);
 
   // ---- plan tables: once per CTA
   for (int i = threadIdx.x; i < D::NY * D::NZ; i += blockDim.x)
@@ -737,16 +781,76 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
   {
     double* p = reinterpret_cast<double*>(wraw + (size_t)warp * pwb);
     m.J = p;   p += D::NW * D::LD;
-    m.R = p;   p += D::NW * D::LD;
+    m.R = p;   p += D::RSZ;
     m.Y = p;   p += 3 * D::NYP;
     m.w = p;   p += D::NW;
     m.d = p;   p += D::NW + 2;
     m.zb = p;  p += D::NW;
     m.items = reinterpret_cast<unsigned short*>(p);
-    seg_ofs = sfo + 40 + warp * 32;
+    seg_ofs = sfo0 + 40 * SAB_COPIES + warp * 32;
   }
   __syncthreads();
   const int n_prob = a.n_prob;
+#if FQ_WARP_ADOPT
+  (void)s_prob;
+  double* sAb = sAb0 + (size_t)warp * 4 * a.max_faces;
+  int* sfo = sfo0 + 40 * warp;
+  const long long me = (long long)blockIdx.x * W + warp, adopters = (long long)gridDim.x * W;
+  const int cursor = (int)((me * n_prob) / adopters);            // warp-specific starting problem
+  int visited = 0;
+  for (;;)
+  {
+    // ---- adopt the next problem (cyclically from `cursor`) that still has unclaimed candidates
+    int found = -1;
+    while (visited < n_prob && found < 0)
+    {
+      const int j = visited + lane;
+      int pj = cursor + j;
+      if (pj >= n_prob) pj -= n_prob;
+      bool open = false;
+      if (j < n_prob)
+        open = *reinterpret_cast<volatile int*>(counters + pj) < a.cand_ofs[pj + 1] - a.cand_ofs[pj];
+      const unsigned bal = __ballot_sync(FULL, open);
+      if (bal) { const int first = __ffs(bal) - 1; found = cursor + visited + first; visited += first + 1; }
+      else visited += 32;
+    }
+    if (found < 0) break;
+    const int prob = found >= n_prob ? found - n_prob : found;
+    const int c_begin = a.cand_ofs[prob], count = a.cand_ofs[prob + 1] - c_begin;
+    const int p0 = a.poly_ofs[prob], P = a.poly_ofs[prob + 1] - p0;
+    const int f0 = a.face_ofs[p0];
+    const int nf = P > 0 ? a.face_ofs[p0 + P] - f0 : 0;
+    bool rows_bad = false;
+    {
+      const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
+      double2* dst = reinterpret_cast<double2*>(sAb);
+      int bad = 0;
+      for (int i = lane; i < 2 * nf; i += 32)
+      {
+        double2 v = src[i];
+        bad |= !(fabs(v.x) < 1e300) || !(fabs(v.y) < 1e300);
+        if (i & 1) v.y += FQ_ROW_TOL;              // rows are staged as [Ax Ay Az b+tol]
+        dst[i] = v;
+      }
+      for (int i = lane; i <= P && i < 36; i += 32) sfo[i] = a.face_ofs[p0 + i] - f0;
+      rows_bad = __any_sync(FULL, bad) != 0;
+      __syncwarp();                                // publishes the staged rows to the warp
+    }
+    int c = 0;
+    if (lane == 0) c = atomicAdd(counters + prob, 1);
+    c = __shfl_sync(FULL, c, 0);
+    while (c < count)
+    {
+      int cn = 0;
+      if (lane == 0) cn = atomicAdd(counters + prob, 1);
+      solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, c_begin + (count - 1 - c), lane, rows_bad);
+      c = __shfl_sync(FULL, cn, 0);
+    }
+    __syncwarp();
+  }
+#else
+  double* sAb = sAb0;
+  int* sfo = sfo0;
   int cursor = (int)(((long long)blockIdx.x * n_prob) / gridDim.x);   // CTA-specific starting problem
   int visited = 0;
   for (;;)
@@ -808,14 +912,15 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
     }
     __syncthreads();                               // everyone is done with the staged rows
   }
+#endif
 }
 
 template <int N_, bool WHOLE_>
-size_t smem_bytes_t(int max_faces, int item_cap)
+size_t smem_bytes_t(int max_faces, int item_cap, int sab_copies = (FQ_WARP_ADOPT ? W : 1))
 {
   using D = Dims<N_, WHOLE_>;
-  return (size_t)8 * (4 * max_faces + D::NY * D::TZLD + D::NY) + (size_t)W * per_warp_bytes<D>(item_cap) +
-         (40 + W * 32) * 4 + 16;
+  return (size_t)8 * ((size_t)sab_copies * 4 * max_faces + D::NY * D::TZLD + D::NY) + (size_t)W * per_warp_bytes<D>(item_cap) +
+         (40 * sab_copies + W * 32) * 4 + 16;
 }
 
 // `counters`: a.n_prob ints of device memory, zeroed here on `stream`

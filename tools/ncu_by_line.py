@@ -45,12 +45,17 @@ assert lines_of, "kernel not found in any cubin"
 
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source=sass"], capture_output=True, text=True).stdout
 blocks = out.split('"Kernel Name"')
-blk = '"Kernel Name"' + blocks[1 + launch]
-rows = list(csv.reader(io.StringIO(blk)))
-hdr = rows[1]
+# newer ncu versions print more than one block per launch: take the launch-th block whose SASS length matches the cubin's
+match = []
+for b in blocks[1:]:
+    rows = list(csv.reader(io.StringIO('"Kernel Name"' + b)))
+    hdr = rows[1]
+    body = [r for r in rows[2:] if len(r) == len(hdr)]
+    if len(body) == len(lines_of) and "Instructions Executed" in hdr:
+        match.append((hdr, body))
+assert match, "no block of the report has %d instructions" % len(lines_of)
+hdr, body = match[min(launch, len(match) - 1)]
 ci = {h: i for i, h in enumerate(hdr)}
-body = [r for r in rows[2:] if len(r) == len(hdr)]
-assert len(body) == len(lines_of), (len(body), len(lines_of))
 agg = defaultdict(lambda: [0, 0, 0, 0])
 tot = [0, 0, 0, 0]
 for (line, sass), r in zip(lines_of, body):
