@@ -16,10 +16,11 @@
 //     |z|^2 < 0.01 |g|^2), nothing has to be initialised per candidate, and leaving rows rotate columns as before;
 //   * duals, the triangular solve and the ratio test are register/shuffle based (element k of an NW-vector lives in
 //     lane k%32, slot k/32); reciprocals and square roots use the MUFU seed + Newton steps instead of IEEE division;
-//   * persistent CTAs: per-problem claim counters in global memory; a CTA adopts a problem that still has unclaimed
-//     candidates, stages its polytope rows once ([Ax Ay Az b+tol], checked for non-finite values), and its warps claim
-//     candidates one at a time, so nobody idles behind a slow candidate and block barriers happen only when a CTA
-//     changes problem;
+//   * persistent CTAs, warp-independent: per-problem claim counters in global memory; every warp adopts a problem that
+//     still has unclaimed candidates, stages its polytope rows into its own copy ([Ax Ay Az b+tol], checked for
+//     non-finite values), and claims candidates one at a time from the end of the problem's list, so nobody idles behind
+//     a slow candidate and no block barrier follows the staging of the plan tables; the triangular factor R is stored
+//     packed, which is what leaves room for the four row copies at 4 CTAs per SM;
 //   * non-finite or non-positive inputs make a candidate "not solved" up front (NaN rank keys would look satisfied).
 #pragma once
 
