@@ -14,7 +14,8 @@
 #define FQ_BACKSUB_PRESCALED 1   // measured +1.0 % (tools/ab.sh, same box); 0 keeps the division on the chain
 #endif
 #ifndef FQ_PACKED_R
-#define FQ_PACKED_R 1         // 1: the triangular factor R is stored packed (column k at k(k+1)/2), half the bytes;
+#define FQ_PACKED_R 1         // 1: the triangular factor R is stored packed (column k at k(k+1)/2), half the bytes
+                              // (2: only in the safe-mode kernels, whose shared memory needs it -- not yet measured);
                               // measured alone -2.4 % (index arithmetic), but it is what makes room for FQ_WARP_ADOPT
 #endif
 #ifndef FQ_WARP_ADOPT

@@ -43,11 +43,12 @@ struct Dims
   static constexpr int TZLD = NZ | 1;            // odd row stride of TZ in shared memory
   static constexpr int SLOTS = (NW + 31) / 32;   // elements of an NW-vector per lane
   static constexpr int RPL = (NY + 31) / 32;     // Y rows per lane
-  static constexpr int RSZ = FQ_PACKED_R ? NW * (NW + 1) / 2 : NW * LD;   // doubles of the triangular factor
+  static constexpr bool PACKED = FQ_PACKED_R == 2 ? !WHOLE_ : (FQ_PACKED_R != 0);   // 2: only where the room is needed
+  static constexpr int RSZ = PACKED ? NW * (NW + 1) / 2 : NW * LD;        // doubles of the triangular factor
   static constexpr int JR = NW * LD + RSZ;                                // J then R, contiguous
   static constexpr int PER_WARP_DOUBLES = JR + 3 * NYP + 3 * NW + 2;
   // element (row j, column k), j <= k, of R
-  __host__ __device__ static constexpr int ri(int j, int k) { return FQ_PACKED_R ? (k * (k + 1)) / 2 + j : k * LD + j; }
+  __host__ __device__ static constexpr int ri(int j, int k) { return PACKED ? (k * (k + 1)) / 2 + j : k * LD + j; }
 };
 // per-warp bytes: solver state + item list (item_cap 16-bit entries)
 template <class D>
@@ -155,35 +156,39 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
                                          double (&rdinv)[D::SLOTS])
 {
   constexpr int LD = D::LD;
-#if FQ_PACKED_R
-  // The columns right of l move one place left and become upper Hessenberg: the element below the new diagonal of
-  // column k is the OLD diagonal of column k+1.  Packed storage has no room for it, so each lane keeps the old diagonal
-  // of "its" column in a register; rotation j reads it by shuffle (no earlier rotation touches row j+1).
   double dg[D::SLOTS];
-#pragma unroll
-  for (int s = 0; s < D::SLOTS; s++)
+  if constexpr (D::PACKED)
   {
-    const int k = lane + 32 * s;
-    dg[s] = k < q ? m.R[D::ri(k, k)] : 0.0;
-  }
-  __syncwarp();
+    // The columns right of l move one place left and become upper Hessenberg: the element below the new diagonal of
+    // column k is the OLD diagonal of column k+1.  Packed storage has no room for it, so each lane keeps the old
+    // diagonal of "its" column in a register; rotation j reads it by shuffle (no earlier rotation touches row j+1).
 #pragma unroll
-  for (int s = 0; s < D::SLOTS; s++)
-  {
-    const int j = lane + 32 * s;                 // this lane moves row j of every column that keeps a row j
-    if (j < q)
-      for (int k = (l > j ? l : j); k < q - 1; k++) m.R[D::ri(j, k)] = m.R[D::ri(j, k + 1)];
-  }
-#else
-  // R: columns l+1..q-1 move left (each lane moves its own rows)
+    for (int s = 0; s < D::SLOTS; s++)
+    {
+      const int k = lane + 32 * s;
+      dg[s] = k < q ? m.R[D::ri(k, k)] : 0.0;
+    }
+    __syncwarp();
 #pragma unroll
-  for (int s = 0; s < D::SLOTS; s++)
-  {
-    const int j = lane + 32 * s;
-    if (j < q)
-      for (int k = l; k < q - 1; k++) m.R[k * LD + j] = m.R[(k + 1) * LD + j];
+    for (int s = 0; s < D::SLOTS; s++)
+    {
+      const int j = lane + 32 * s;                 // this lane moves row j of every column that keeps a row j
+      if (j < q)
+        for (int k = (l > j ? l : j); k < q - 1; k++) m.R[D::ri(j, k)] = m.R[D::ri(j, k + 1)];
+    }
   }
-#endif
+  else
+  {
+    // R: columns l+1..q-1 move left (each lane moves its own rows)
+#pragma unroll
+    for (int s = 0; s < D::SLOTS; s++)
+    {
+      const int j = lane + 32 * s;
+      dg[s] = 0.0;
+      if (j < q)
+        for (int k = l; k < q - 1; k++) m.R[k * LD + j] = m.R[(k + 1) * LD + j];
+    }
+  }
   // lam: element k <- element k+1 for k in [l, q-1)
   {
     double nxt[D::SLOTS];
@@ -204,13 +209,14 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
   __syncwarp();
   for (int j = l; j < q - 1; j++)
   {
-#if FQ_PACKED_R
-    const double p = m.R[D::ri(j, j)];
-    const int js = (j + 1) >> 5;
-    const double sb = __shfl_sync(FULL, (D::SLOTS > 1 && js == 1) ? dg[D::SLOTS - 1] : dg[0], (j + 1) & 31);
-#else
-    const double p = m.R[j * LD + j], sb = m.R[j * LD + j + 1];
-#endif
+    double p, sb;
+    if constexpr (D::PACKED)
+    {
+      p = m.R[D::ri(j, j)];
+      const int js = (j + 1) >> 5;
+      sb = __shfl_sync(FULL, (D::SLOTS > 1 && js == 1) ? dg[D::SLOTS - 1] : dg[0], (j + 1) & 31);
+    }
+    else { p = m.R[j * LD + j]; sb = m.R[j * LD + j + 1]; }
     const double h2 = fma(p, p, sb * sb);
     double c = 1.0, sn = 0.0, hi = 0.0;
     if (h2 > 0) { hi = fast_rsqrt(h2); c = p * hi; sn = sb * hi; }
@@ -219,23 +225,26 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
     for (int s = 0; s < D::SLOTS; s++)
     {
       const int k = lane + 32 * s;
-#if FQ_PACKED_R
-      if (k > j && k < q - 1)
-      { // rows j, j+1 of R at column k (both inside the triangle)
-        const double u = m.R[D::ri(j, k)], v = m.R[D::ri(j + 1, k)];
-        m.R[D::ri(j, k)] = fma(c, u, sn * v);
-        m.R[D::ri(j + 1, k)] = fma(c, v, -sn * u);
+      if constexpr (D::PACKED)
+      {
+        if (k > j && k < q - 1)
+        { // rows j, j+1 of R at column k (both inside the triangle)
+          const double u = m.R[D::ri(j, k)], v = m.R[D::ri(j + 1, k)];
+          m.R[D::ri(j, k)] = fma(c, u, sn * v);
+          m.R[D::ri(j + 1, k)] = fma(c, v, -sn * u);
+        }
+        if (k == j) { m.R[D::ri(j, j)] = fma(c, p, sn * sb); rdinv[s] = hi; }   // the element below it rotates to zero
       }
-      if (k == j) { m.R[D::ri(j, j)] = fma(c, p, sn * sb); rdinv[s] = hi; }     // the element below it rotates to zero
-#else
-      if (k >= j && k < q - 1)
-      { // rows j, j+1 of R at column k
-        const double u = m.R[k * LD + j], v = m.R[k * LD + j + 1];
-        m.R[k * LD + j] = fma(c, u, sn * v);
-        m.R[k * LD + j + 1] = fma(c, v, -sn * u);
+      else
+      {
+        if (k >= j && k < q - 1)
+        { // rows j, j+1 of R at column k
+          const double u = m.R[k * LD + j], v = m.R[k * LD + j + 1];
+          m.R[k * LD + j] = fma(c, u, sn * v);
+          m.R[k * LD + j + 1] = fma(c, v, -sn * u);
+        }
+        if (k == j) rdinv[s] = hi;                 // new diagonal is h = sqrt(h2)
       }
-      if (k == j) rdinv[s] = hi;                 // new diagonal is h = sqrt(h2)
-#endif
       if (k < D::NW)
       { // columns j, j+1 of J at row k
         const double u = m.J[k * LD + j], v = m.J[k * LD + j + 1];
