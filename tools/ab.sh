@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of library variants on ONE box (run under gpurun): tools/ab.sh lib1.so lib2.so ...  (names under faster_b200/lib)
 # Each variant: bench.py resident + e2e numbers and the oracle parity check; two rounds to see the noise.
-for round in 1 2; do
+for round in $(seq 1 ${AB_ROUNDS:-2}); do
   for lib in "$@"; do
     FQ_LIB=$PWD/faster_b200/lib/$lib python bench.py --steps 60 --cpu-seconds 0.5 > gpurun_out/ab_tmp.json 2>/dev/null
     python - "$lib" <<'PY'
