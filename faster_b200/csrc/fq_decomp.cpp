@@ -86,6 +86,24 @@ struct Ellip
   }
 };
 
+// E.dist for n points given as separate coordinate arrays: the same operations in the same order as Ellip::dist (packed
+// IEEE divisions and square roots round like the scalar ones; the avx2 clone has no FMA), four points per instruction
+__attribute__((target_clones("avx2", "default")))
+void dist_batch(const Ellip& E, int n, const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ Z,
+                double* __restrict__ out)
+{
+  const double r00 = E.Rf.m[0][0], r01 = E.Rf.m[0][1], r02 = E.Rf.m[0][2], r10 = E.Rf.m[1][0], r11 = E.Rf.m[1][1],
+               r12 = E.Rf.m[1][2], r20 = E.Rf.m[2][0], r21 = E.Rf.m[2][1], r22 = E.Rf.m[2][2];
+  const double dx = E.d.x, dy = E.d.y, dz = E.d.z, a0 = E.ax[0], a1 = E.ax[1], a2 = E.ax[2];
+  for (int i = 0; i < n; i++)
+  {
+    const double vx = X[i] - dx, vy = Y[i] - dy, vz = Z[i] - dz;
+    const double qx = r00 * vx + r10 * vy + r20 * vz, qy = r01 * vx + r11 * vy + r21 * vz, qz = r02 * vx + r12 * vy + r22 * vz;
+    const double a = qx / a0, b = qy / a1, c = qz / a2;
+    out[i] = std::sqrt(a * a + b * b + c * c);
+  }
+}
+
 // first strict minimum of dist over the listed indices (ellipsoid.h:46-60)
 int closest(const Ellip& E, const std::vector<V3>& pts, const std::vector<int>& idx)
 {
@@ -115,15 +133,37 @@ void local_bbox(V3 p1, V3 p2, const double* bbox, Plane out[6])
   out[5] = { p1 - dir_v * bbox[2], dir_v * -1.0 };
 }
 
+// axis-aligned hull of the oriented box bb[0..5] of local_bbox (padded by 1e-6, far beyond the 1e-10 of the exact test)
+void bbox_aabb(V3 p1, const Plane bb[6], double lo[3], double hi[3])
+{
+  for (int k = 0; k < 3; k++) { lo[k] = 1e300; hi[k] = -1e300; }
+  for (int c = 0; c < 8; c++)
+  { // a corner adds to p1 the displacement of one face point of each opposite pair (the three axes are orthogonal)
+    const Plane& fh = bb[(c & 1) ? 0 : 1];
+    const Plane& fd = bb[(c & 2) ? 2 : 3];
+    const Plane& fv = bb[(c & 4) ? 4 : 5];
+    const V3 corner = p1 + (fh.p - p1) + (fd.p - p1) + (fv.p - p1);
+    const double cc[3] = { corner.x, corner.y, corner.z };
+    for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], cc[k]); hi[k] = std::fmax(hi[k], cc[k]); }
+  }
+  for (int k = 0; k < 3; k++) { lo[k] -= 1e-6; hi[k] += 1e-6; }
+}
+
 void decompose_segment(V3 p1, V3 p2, const double* obs, int n_obs, const double* bbox, double inflate, std::vector<Plane>* planes)
 {
   Plane bb[6];
   local_bbox(p1, p2, bbox, bb);
   // set_obs (decomp_base.h:39-46 / polyhedron.h:65-76): keep points with signed_dist <= epsilon_ for every bbox face
+  // A cheap conservative reject first: the axis-aligned box around the eight corners of the oriented one, padded well
+  // beyond epsilon_ (most of a map's points fail it after one or two comparisons); survivors get the exact test.
+  double lo[3], hi[3];
+  bbox_aabb(p1, bb, lo, hi);
   std::vector<V3> O;
   for (int i = 0; i < n_obs; i++)
   {
-    const V3 pt = { obs[3 * i], obs[3 * i + 1], obs[3 * i + 2] };
+    const double x = obs[3 * i], y = obs[3 * i + 1], z = obs[3 * i + 2];
+    if (x < lo[0] || x > hi[0] || y < lo[1] || y > hi[1] || z < lo[2] || z > hi[2]) continue;
+    const V3 pt = { x, y, z };
     bool in = true;
     for (int k = 0; k < 6 && in; k++) in = !(dot(bb[k].n, pt - bb[k].p) > kEps);
     if (in) O.push_back(pt);
@@ -139,9 +179,15 @@ void decompose_segment(V3 p1, V3 p2, const double* obs, int n_obs, const double*
     p = { p.x - sgn(p.x) * inflate, p.y - sgn(p.y) * inflate, p.z - sgn(p.z) * inflate };
     it = mul(Ri, p) + E.d;
   }
+  // coordinate arrays of the (inflated) points for the two passes that evaluate the distance of EVERY point
+  const int nO = (int)O.size();
+  std::vector<double> soa((size_t)4 * nO);
+  double *OX = soa.data(), *OY = OX + nO, *OZ = OY + nO, *dist_of = OZ + nO;
+  for (int i = 0; i < nO; i++) { OX[i] = O[i].x; OY[i] = O[i].y; OZ[i] = O[i].z; }
+  dist_batch(E, nO, OX, OY, OZ, dist_of);
   std::vector<int> inside0, cur;
-  for (int i = 0; i < (int)O.size(); i++)
-    if (E.dist(O[i]) <= 1) inside0.push_back(i);
+  for (int i = 0; i < nO; i++)
+    if (dist_of[i] <= 1) inside0.push_back(i);
   cur = inside0;
   while (!cur.empty())
   { // shrink the two short axes together (:195-217)
@@ -175,9 +221,16 @@ void decompose_segment(V3 p1, V3 p2, const double* obs, int n_obs, const double*
   // find_polyhedron (decomp_base.h:83-115): tangent half-spaces at successive closest points
   std::vector<int> remain(O.size());
   for (int i = 0; i < (int)O.size(); i++) remain[i] = i;
+  // the ellipsoid is final here: every point's distance is evaluated once (the same value the reference recomputes in
+  // every round), and a round is an arg-min over the survivors plus one half-space test per survivor
+  dist_batch(E, nO, OX, OY, OZ, dist_of);
   while (!remain.empty())
   {
-    const V3 cp = O[closest(E, O, remain)];
+    int best = -1;
+    double bd = 1.7976931348623157e308;
+    for (int i : remain)
+      if (dist_of[i] < bd) { bd = dist_of[i]; best = i; }     // first strict minimum, as closest()
+    const V3 cp = O[best];
     // n = C^-1 C^-T (cp - d) = Rf diag(1/ax^2) Rf' (cp - d), normalised  (ellipsoid.h:65-73)
     V3 q = mulT(E.Rf, cp - E.d);
     q = { q.x / (E.ax[0] * E.ax[0]), q.y / (E.ax[1] * E.ax[1]), q.z / (E.ax[2] * E.ax[2]) };
@@ -199,6 +252,32 @@ extern "C" int fq_ellipsoid_decomp(const double* path, int n_seg, const double* 
   if (!path || n_seg < 1 || n_obs < 0 || (n_obs > 0 && !obs) || !bbox || !face_ofs || !Ab) return FQ_E_ARG;
   int rows = 0;
   face_ofs[0] = 0;
+  // With several segments every point would be looked at once per segment; one pass against the hull of ALL the
+  // segments' boxes first leaves each segment a short list (a map is much larger than a corridor).
+  std::vector<double> near_pts;
+  if (n_seg > 1 && n_obs > 256)
+  {
+    double ulo[3] = { 1e300, 1e300, 1e300 }, uhi[3] = { -1e300, -1e300, -1e300 };
+    for (int s = 0; s < n_seg; s++)
+    {
+      const V3 p1 = { path[3 * s], path[3 * s + 1], path[3 * s + 2] }, p2 = { path[3 * s + 3], path[3 * s + 4], path[3 * s + 5] };
+      if (norm(p2 - p1) == 0) return FQ_E_ARG;
+      Plane bb[6];
+      double lo[3], hi[3];
+      local_bbox(p1, p2, bbox, bb);
+      bbox_aabb(p1, bb, lo, hi);
+      for (int k = 0; k < 3; k++) { ulo[k] = std::fmin(ulo[k], lo[k]); uhi[k] = std::fmax(uhi[k], hi[k]); }
+    }
+    near_pts.reserve((size_t)3 * (n_obs / 4 + 16));
+    for (int i = 0; i < n_obs; i++)
+    {
+      const double x = obs[3 * i], y = obs[3 * i + 1], z = obs[3 * i + 2];
+      if (x < ulo[0] || x > uhi[0] || y < ulo[1] || y > uhi[1] || z < ulo[2] || z > uhi[2]) continue;
+      near_pts.push_back(x); near_pts.push_back(y); near_pts.push_back(z);      // order preserved
+    }
+    obs = near_pts.data();
+    n_obs = (int)(near_pts.size() / 3);
+  }
   std::vector<Plane> planes;
   for (int s = 0; s < n_seg; s++)
   {

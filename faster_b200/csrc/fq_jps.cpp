@@ -143,7 +143,17 @@ struct Node
 class Search
 {
 public:
-  Search(const Grid& g, V3i goal) : g_(g), goal_(goal), cell_(g.xd * (size_t)g.yd * g.zd, -1) {}
+  // The cell -> node index map is as large as the grid (a few hundred thousand cells) while a search touches a few
+  // hundred of them: it lives in a per-thread buffer whose entries carry the number of the search that wrote them, so
+  // nothing is cleared between searches.
+  Search(const Grid& g, V3i goal) : g_(g), goal_(goal), cell_(scratch().cell), stamp_(scratch().stamp)
+  {
+    const size_t n = g.xd * (size_t)g.yd * g.zd;
+    Scratch& sc = scratch();
+    if (sc.cell.size() < n) { sc.cell.assign(n, -1); sc.stamp.assign(n, 0u); sc.epoch = 0; }
+    if (++sc.epoch == 0) { std::fill(sc.stamp.begin(), sc.stamp.end(), 0u); sc.epoch = 1; }
+    epoch_ = sc.epoch;
+  }
 
   // priority: smaller f first; equal f (within 1e-6): larger g first (graph_search.h:19-27)
   bool lower(int a, int b) const
@@ -195,9 +205,11 @@ public:
   }
   int node_at(int x, int y, int z, V3i dir)
   {
-    int& c = cell_[g_.id(x, y, z)];
-    if (c < 0)
+    const int cid = g_.id(x, y, z);
+    int& c = cell_[cid];
+    if (stamp_[cid] != epoch_)
     {
+      stamp_[cid] = epoch_;
       c = (int)n_.size();
       n_.push_back({ x, y, z, dir, -1, INFINITY, heur(x, y, z), -1 });
     }
@@ -291,7 +303,20 @@ public:
 private:
   Grid g_;
   V3i goal_;
-  std::vector<int> cell_;
+  struct Scratch
+  {
+    std::vector<int> cell;
+    std::vector<unsigned> stamp;
+    unsigned epoch = 0;
+  };
+  static Scratch& scratch()
+  {
+    static thread_local Scratch s;
+    return s;
+  }
+  std::vector<int>& cell_;
+  std::vector<unsigned>& stamp_;
+  unsigned epoch_ = 0;
   std::vector<Node> n_;
   std::vector<int> heap_;
 };
