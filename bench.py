@@ -396,6 +396,12 @@ def main():
                     "issue_active_pct": float(np.mean([l["issue_active_pct"] for l in ls])),
                     "warp_instructions_per_candidate": float(np.mean([l["warp_instructions"] for l in ls]) / n_cand),
                     "source": pj["label"]}
+            if all("lsu_data_pipe_pct_of_peak" in l for l in ls):
+                # the unit this kernel loads most: the L1/shared-memory data pipe (ncu, % of peak over the elapsed launch)
+                prof["shared_memory_pipe"] = {
+                    "pct_of_peak": float(np.mean([l["lsu_data_pipe_pct_of_peak"] for l in ls])),
+                    "pct_of_peak_while_sm_active": float(np.mean([l["lsu_data_pipe_pct_of_peak_while_sm_active"] for l in ls])),
+                    "metric": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"}
             if all("fp64_flops" in l for l in ls):
                 # executed FP64 flops per launch (ncu counters) over the live launch time, against the NOMINAL FP64 peak
                 fl = float(np.mean([l["fp64_flops"] for l in ls]))
@@ -429,7 +435,7 @@ def main():
                              "ncu": prof,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                              "algorithmic_bytes_per_candidate": BYTES_PER_CAND,
-                             "note": "compute/latency-bound FP64 kernel; HBM fraction is tiny by construction (SURVEY 8d)"}}
+                             "note": "HBM fraction is tiny by construction (SURVEY 8d); the nearest hardware limit is the shared-memory data pipe (see ncu.shared_memory_pipe), then FP64 issue"}}
         line["config"]["iteration_cap_hits"] = int((torch.cat([outs_d[0][2], outs_d[1][2]]) < 0).sum())
         if not args.no_cpu_baseline:
             # checker: the first corridors of this very workload re-solved by the CPU restatement

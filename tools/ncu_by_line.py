@@ -77,8 +77,9 @@ def srcline(key):
     L = _srcs[f]
     return "%s:%d %s" % (f.replace("fq_kernels", "k"), n, L[n - 1].strip()[:80] if n <= len(L) else "?")
 print("total warp-inst %d  stall samples %d  smem wavefronts %d (excess %d)" % (tot[0], tot[1], tot[3], tot[2]))
-for key, name in ((0, "instructions executed"), (1, "stall samples")):
+for key, name in ((0, "instructions executed"), (1, "stall samples"), (3, "shared-memory wavefronts")):
     print("---- top lines by", name)
     for line, v in sorted(agg.items(), key=lambda kv: -kv[1][key])[:top]:
-        print("inst %5.1f%% stall %5.1f%% smem-excess %5.1f%% | %s" % (100.0 * v[0] / tot[0], 100.0 * v[1] / max(1, tot[1]),
-                                                              100.0 * v[2] / max(1, tot[2]), srcline(line)))
+        print("inst %5.1f%% stall %5.1f%% smem-wavefronts %5.1f%% smem-excess %5.1f%% | %s" %
+              (100.0 * v[0] / tot[0], 100.0 * v[1] / max(1, tot[1]), 100.0 * v[3] / max(1, tot[3]), 100.0 * v[2] / max(1, tot[2]),
+               srcline(line)))

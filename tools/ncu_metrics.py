@@ -36,6 +36,11 @@ for r in body:
         "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
         "fp64_pipe_active_pct": val(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
         "smem_bank_conflict_wavefronts": val(r, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+        "smem_wavefronts": val(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+        "lsu_data_pipe_pct_of_peak": val(r, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+        "sm_cycles_elapsed_avg": val(r, "sm__cycles_elapsed.avg"),
+        "sm_cycles_active_avg": val(r, "sm__cycles_active.avg"),
+        "sm_cycles_active_max": val(r, "sm__cycles_active.max"),
     })
 json.dump({"label": label, "report": rep, "note": "values under ncu replay (cold cache, serialised); per launch",
            "launches": launches}, open(out, "w"), indent=1)
