@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- candidate (whole+safe pair) trajectory solves per second.
+"""bench.py -- candidate (whole+safe pair) trajectory solves per second on BASELINE.json's configurations.
 
-Workload ("cfg2-pairs"): C corridor problems per GPU; each contributes BASELINE config 2's whole batch
-(N=10, 3 polytopes, 1024 candidates = 16 time allocations x 64 monotone assignments, final position pinned) and a
-safe batch of the same size shaped like config 3 (N=10, 4 polytopes, forceFinalConstraint=false, 16 x 64 of the 286
-monotone assignments).  A "pair" is one whole + one safe candidate solve; a step solves C x 1024 pairs per GPU.
-Multi-GPU: corridors are sharded by rank (weak scaling), one all-gather of the per-candidate costs per step.
+Default workload = BASELINE config 4 as written: random-forest corridors (JPS3D + convex decomposition on the host,
+committed as bench_data/cfg4_forest.npz by tools/make_cfg4_fixture.py), PAIRED whole + safe solve: per corridor the
+whole sweep (N=10, 3 polytopes, 16 time allocations x 64 assignments = 1024 candidates, final position pinned), the
+genNewTraj selection, R = sample (int)(0.6 n) of the winner, then the safe sweep FROM R (N=10, 4 polytopes, 1024
+candidates, final position free) -- two dependent launches per batch, chained on the device (fq_replan_pairs_dev).
+One pass = 64 corridors = 65 536 pairs per GPU; one step = --inner passes over a ring of distinct batches.
 
-value : pairs/s with all inputs resident in HBM (two launches of fq_solve_kernel per step, CUDA-event timed).
-e2e   : pairs/s through the host-pointer C ABI (fq_solve_multi) from pinned host buffers, H2D + D2H inside.
+value : pairs/s, inputs resident in HBM, CUDA-event timed, max over ranks.  N > 1: every rank runs its own 64 corridors
+        per pass (weak scaling) and every chain ends with the path's one collective, an NCCL all-gather of the
+        per-corridor result records inside the library; "strong" reports the same 65 536 pairs split over the ranks.
+e2e   : the same through the host-pointer C ABI (fq_replan_pairs_async on two contexts) from pinned host arrays.
+other_configs : BASELINE configs 2, 3 and 5 as written (single-kind batches), each with kernel time, roofline, parity.
+--impl reference : the CPU arm (Gurobi itself is unavailable): the CPU port of the same chain on all host threads.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -24,45 +30,98 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_SEG = 10
-N_DT = 16
-N_SIG = 64
-CAND = N_DT * N_SIG
-BYTES_PER_CAND = 8 * (9 + 9 + 3 + 1) + N_SEG + 1 + 8        # x0,xf,lim,dt + sigma + flag + cost = 195 B
+BYTES_PER_CAND = {10: 8 * (9 + 9 + 3 + 1) + 10 + 1 + 8, 15: 8 * (9 + 9 + 3 + 1) + 15 + 1 + 8}   # 195 / 200 B
+METRIC = "candidate (whole+safe pair) trajectory solves/sec"
+CFG4_NAME = ("cfg4: random-forest corridors (host JPS3D + convex decomposition), paired whole (N=10, P=3) + safe (N=10, P=4, "
+             "x0 = whole winner's sample at 60 % of the horizon) solve, 64 corridors x 1024 pairs = 65 536 pairs per pass")
+FIXTURE = os.path.join(ROOT, "bench_data", "cfg4_forest.npz")
+PAIR_KEYS = ["x0", "xf_whole", "xf_safe", "lim", "poly_ofs_whole", "face_ofs_whole", "Ab_whole", "poly_ofs_safe",
+             "face_ofs_safe", "Ab_safe", "factors_whole", "sigmas_whole", "factors_safe", "sigmas_safe"]
 
 
-def make_workload(n_corr, seed0, kind):
-    """kind 'whole' (P=3, force_final) or 'safe' (P=4, free final position).  Returns dict of numpy arrays laid out
-    for fq_solve_multi."""
-    from faster_b200 import capi, corridor as cr
-    P, ff = (3, True) if kind == "whole" else (4, False)
-    sig_all = cr.monotone_sigmas(N_SEG, P)
-    idx = np.linspace(0, len(sig_all) - 1, N_SIG).round().astype(int)
-    sig = sig_all[idx]
+# ----------------------------------------------------------------------------------------------------------------------
+# workloads (numpy only: both arms use these)
+# ----------------------------------------------------------------------------------------------------------------------
+_fx = None
+
+
+def load_cfg4(start, count):
+    """Corridors [start, start+count) (cyclic) of the committed config-4 fixture as a pair-workload dict (the layout of
+    fq_pair_args; see faster_b200.capi.make_pair_workload)."""
+    global _fx
+    if _fx is None:
+        _fx = dict(np.load(FIXTURE))
+    f = _fx
+    n_all = int(f["meta"][0])
+    idx = [(start + i) % n_all for i in range(count)]
+
+    def sub(po, fo, Ab):
+        npo, nfo, rows = [0], [0], []
+        for j in idx:
+            for p in range(po[j], po[j + 1]):
+                rows.append(Ab[fo[p]:fo[p + 1]])
+                nfo.append(nfo[-1] + fo[p + 1] - fo[p])
+            npo.append(npo[-1] + po[j + 1] - po[j])
+        nfo = np.asarray(nfo, np.int32); npo = np.asarray(npo, np.int32)
+        mf = int(max(nfo[npo[j + 1]] - nfo[npo[j]] for j in range(count)))
+        return npo, nfo, np.ascontiguousarray(np.vstack(rows)), mf, int(np.diff(nfo).max())
+    pw, fw, Aw, mfw, mpfw = sub(f["poly_ofs_whole"], f["face_ofs_whole"], f["Ab_whole"])
+    ps, fs, As, mfs, mpfs = sub(f["poly_ofs_safe"], f["face_ofs_safe"], f["Ab_safe"])
+    return dict(n_prob=count, N_whole=int(f["meta"][1]), N_safe=int(f["meta"][2]), DC=float(f["DC"]), r_fraction=float(f["r_fraction"]),
+                x0=np.ascontiguousarray(f["x0"][idx]), xf_whole=np.ascontiguousarray(f["xf_whole"][idx]),
+                xf_safe=np.ascontiguousarray(f["xf_safe"][idx]), lim=np.ascontiguousarray(f["lim"][idx]),
+                poly_ofs_whole=pw, face_ofs_whole=fw, Ab_whole=Aw, poly_ofs_safe=ps, face_ofs_safe=fs, Ab_safe=As,
+                factors_whole=f["factors_whole"].copy(), sigmas_whole=f["sigmas_whole"].copy(),
+                factors_safe=f["factors_safe"].copy(), sigmas_safe=f["sigmas_safe"].copy(),
+                max_faces_whole=mfw, max_poly_faces_whole=mpfw, max_faces_safe=mfs, max_poly_faces_safe=mpfs,
+                R_oracle=np.ascontiguousarray(f["R_oracle"][idx]))
+
+
+def pairs_per_pass(w):
+    return w["n_prob"] * len(w["factors_whole"]) * len(w["sigmas_whole"])
+
+
+SINGLE = {   # BASELINE configs 2, 3, 5 as SURVEY 8(d) specifies them
+    "cfg2": dict(name="cfg2: whole-trajectory QP, N=10, 3 polytopes, 1024 candidates per corridor (16 dt x 64 sigma)",
+                 N=10, P=3, ff=True, profile="uav", n_dt=16, n_sig=64, corridors=64, seed=2000),
+    "cfg3": dict(name="cfg3: safe-trajectory MIQP candidates, N=10, 4 polytopes, 8192 per corridor (32 dt x 256 sigma)",
+                 N=10, P=4, ff=False, profile="uav", n_dt=32, n_sig=256, corridors=8, seed=3000),
+    "cfg5": dict(name="cfg5: ground robot (v 1.4, a 1.4, j 5.0), N=15, 8 narrow polytopes, 32 768 per corridor (16 dt x 2048 sampled sigma)",
+                 N=15, P=8, ff=True, profile="ground", n_dt=16, n_sig=2048, corridors=2, seed=5000),
+}
+
+
+def make_single(cfg, n_corr, dt_initial):
+    """Synthetic corridors of a single-kind configuration laid out for fq_solve_multi.  dt_initial(x0, xf, lim, N) is the
+    arm's own getDTInitial (product library or oracle), so that neither arm needs the other's code."""
+    from faster_b200 import corridor as cr           # pure numpy module
+    N, P = cfg["N"], cfg["P"]
+    if cfg["n_sig"] >= 1024:
+        sig = cr.sample_monotone_sigmas(N, P, cfg["n_sig"], np.random.default_rng(cfg["seed"]))
+    else:
+        allm = cr.monotone_sigmas(N, P)
+        sig = allm[np.linspace(0, len(allm) - 1, cfg["n_sig"]).round().astype(int)]
+    cand = cfg["n_dt"] * cfg["n_sig"]
     x0 = np.zeros((n_corr, 9)); xf = np.zeros((n_corr, 9)); lim = np.zeros((n_corr, 3))
-    poly_ofs, face_ofs, rows = [0], [0], []
-    dts = np.zeros((n_corr, CAND)); sigs = np.zeros((n_corr, CAND, N_SEG), np.uint8)
-    probs = []
+    po, fo, rows = [0], [0], []
+    dts = np.zeros((n_corr, cand)); sigs = np.zeros((n_corr, cand, N), np.uint8)
     for c in range(n_corr):
-        pb = cr.make_corridor(seed0 + c, P, N_SEG, "uav", ff)
-        probs.append(pb)
+        pb = cr.make_corridor(cfg["seed"] + c, P, N, cfg["profile"], cfg["ff"])
         x0[c], xf[c], lim[c] = pb["x0"], pb["xf"], pb["lim"]
         for A, b in pb["polys"]:
-            rows.append(np.hstack([A, b[:, None]]))
-            face_ofs.append(face_ofs[-1] + len(b))
-        poly_ofs.append(poly_ofs[-1] + P)
-        dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N_SEG)
-        fac = np.arange(1, N_DT + 1, dtype=np.float64)          # factor sweep 1..16 step 1 (faster.cpp:57, yaml:30)
-        dts[c] = np.repeat(fac * max(dti, 2 * pb["DC"]), N_SIG)
-        sigs[c] = np.tile(sig, (N_DT, 1))
-    w = dict(kind=kind, N=N_SEG, ff=ff, n_prob=n_corr, x0=x0, xf=xf, lim=lim,
-             poly_ofs=np.array(poly_ofs, np.int32), face_ofs=np.array(face_ofs, np.int32),
-             Ab=np.ascontiguousarray(np.vstack(rows)), cand_ofs=(np.arange(n_corr + 1) * CAND).astype(np.int32),
-             dt=dts.reshape(-1), sigma=sigs.reshape(-1, N_SEG), probs=probs,
-             max_faces=int(max(face_ofs[poly_ofs[j + 1]] - face_ofs[poly_ofs[j]] for j in range(n_corr))),
-             max_poly_faces=int(np.diff(face_ofs).max()))
-    return w
+            rows.append(np.hstack([A, b[:, None]])); fo.append(fo[-1] + len(b))
+        po.append(po[-1] + P)
+        base = max(dt_initial(pb["x0"], pb["xf"], pb["lim"], N), 2 * pb["DC"])
+        dts[c] = np.repeat(np.arange(1.0, cfg["n_dt"] + 1) * base, cfg["n_sig"])        # factors 1..n_dt (faster.cpp:57)
+        sigs[c] = np.tile(sig, (cfg["n_dt"], 1))
+    fo = np.asarray(fo, np.int32); po = np.asarray(po, np.int32)
+    return dict(N=N, ff=cfg["ff"], n_prob=n_corr, cand=cand, x0=x0, xf=xf, lim=lim, poly_ofs=po, face_ofs=fo,
+                Ab=np.ascontiguousarray(np.vstack(rows)), cand_ofs=(np.arange(n_corr + 1) * cand).astype(np.int32),
+                dt=dts.reshape(-1), sigma=sigs.reshape(-1, N),
+                max_faces=int(max(fo[po[j + 1]] - fo[po[j]] for j in range(n_corr))), max_poly_faces=int(np.diff(fo).max()))
 
 
+# ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -90,79 +149,97 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_reference_rate(n_corr_sample, threads, min_seconds, seed0=900000):
-    """Times the CPU restatement (oracle) on a bounded sample of the same workload.  -> (pairs/s, sample text)."""
-    from oracle import pyoracle as po
-    po.build()
-    ww = make_workload(n_corr_sample, seed0, "whole")
-    ws = make_workload(n_corr_sample, seed0 + 50000, "safe")
+def cfg4_config(world, C):
+    """Identical for both arms (the driver compares the two lines' configs)."""
+    return {"workload": CFG4_NAME, "corridors_per_gpu_per_pass": C, "pairs_per_pass_per_gpu": C * 1024,
+            "l2": "flushed between timed steps (256 MiB memset outside the per-step events); a step cycles through a ring of distinct batches",
+            "parallelism": ("corridor shards per rank + one NCCL all-gather of the per-corridor result records (inside the library)"
+                            if world > 1 else "single GPU")}
 
-    def one_pass():
-        for w in (ww, ws):
-            po.solve_multi(N_SEG, w["ff"], w["x0"], w["xf"], w["lim"], w["poly_ofs"], w["face_ofs"], w["Ab"],
-                           w["cand_ofs"], w["dt"], w["sigma"], threads)
-    one_pass()                                                      # warm-up
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_pair_rate(n_corr, threads, min_seconds, start=256):
+    """The CPU port of the chain on a bounded sample of the same fixture.  -> (pairs/s, sample text)."""
+    from oracle import pair_oracle
+    w = load_cfg4(start, n_corr)
+    pair_oracle.replan_pairs(w, threads)                       # warm-up
     reps, t0 = 0, time.perf_counter()
     while True:
-        one_pass()
+        pair_oracle.replan_pairs(w, threads)
         reps += 1
         el = time.perf_counter() - t0
         if el >= min_seconds and reps >= 2:
             break
-    rate = reps * n_corr_sample * CAND / el
-    return rate, "%d corridors x %d pairs, %d passes, %.1f s" % (n_corr_sample, CAND, reps, el)
+    return reps * pairs_per_pass(w) / el, "%d corridors x 1024 pairs of the cfg4 fixture, %d passes, %.1f s" % (n_corr, reps, el)
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path cannot run (Gurobi is closed source and
-    absent); this times the CPU restatement of it (oracle/fq_oracle.c) on all host threads."""
+    absent); this times the CPU port of it (oracle/) on all host threads, same workload, a bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_s = max(1, args.ref_corridors)
-    from oracle import pyoracle as po
+    from oracle import pyoracle as po, pair_oracle
     po.build()
-    ww = make_workload(n_s, 900000, "whole")
-    ws = make_workload(n_s, 950000, "safe")
-
-    def step():
-        for w in (ww, ws):
-            po.solve_multi(N_SEG, w["ff"], w["x0"], w["xf"], w["lim"], w["poly_ofs"], w["face_ofs"], w["Ab"],
-                           w["cand_ofs"], w["dt"], w["sigma"], threads)
-    for _ in range(args.warmup):
-        step()
+    n_s = max(1, args.ref_corridors)
+    ws = [load_cfg4(256 + n_s * k, n_s) for k in range(4)]
+    for k in range(args.warmup):
+        pair_oracle.replan_pairs(ws[k % 4], threads)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
+    for k in range(args.steps):
+        pair_oracle.replan_pairs(ws[k % 4], threads)
     el = time.perf_counter() - t0
-    value = args.steps * n_s * CAND / el
-    line = {"impl": "reference", "metric": "candidate (whole+safe pair) trajectory solves/sec", "value": value,
-            "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2-pairs: N=10, whole P=3 + safe P=4, 1024 pairs/corridor (16 dt x 64 sigma)",
-                       "corridors_per_step": n_s, "note": "CPU restatement of SolverGurobi (Gurobi itself unavailable)"},
+    value = args.steps * n_s * 1024 / el
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg4_config(args.gpus, args.corridors),
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
-                             "sample": "%d corridors x %d pairs per step" % (n_s, CAND)},
+                             "sample": "%d corridors x 1024 pairs of the cfg4 fixture per step" % n_s,
+                             "note": "CPU restatement of SolverGurobi (Gurobi itself unavailable)"},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+class PairBatch:
+    """One batch of corridors resident on the device + its output arrays, and the PairArgs pointing at them."""
+
+    def __init__(self, w, dev, torch, capi, gather_world=0):
+        self.w = w
+        self.d = {k: torch.from_numpy(np.ascontiguousarray(w[k])).to(dev) for k in PAIR_KEYS}
+        n, nc = w["n_prob"], pairs_per_pass(w)
+        self.out = dict(feasible_whole=torch.zeros(nc, dtype=torch.uint8, device=dev), cost_whole=torch.zeros(nc, dtype=torch.float64, device=dev),
+                        feasible_safe=torch.zeros(nc, dtype=torch.uint8, device=dev), cost_safe=torch.zeros(nc, dtype=torch.float64, device=dev),
+                        results=torch.zeros(n * 144, dtype=torch.uint8, device=dev))
+        self.gathered = torch.zeros(max(1, gather_world) * n * 144, dtype=torch.uint8, device=dev) if gather_world else None
+        self.args = capi.pair_args(w, lambda k: self.d[k].data_ptr(), {k: v.data_ptr() for k, v in self.out.items()})
+
+    def results(self, capi):
+        return np.frombuffer(self.out["results"].cpu().numpy().tobytes(), capi.PAIR_RESULT_DTYPE)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--corridors", type=int, default=64, help="corridor problems per GPU per step")
-    ap.add_argument("--ref-corridors", type=int, default=16, help="corridors per step of the CPU arm (bounded sample)")
+    ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--corridors", type=int, default=64, help="corridors per GPU per pass (cfg4)")
+    ap.add_argument("--inner", type=int, default=48, help="passes per step")
+    ap.add_argument("--ring", type=int, default=8, help="distinct batches a step cycles through")
+    ap.add_argument("--ref-corridors", type=int, default=8, help="corridors per step of the CPU arm (bounded sample)")
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-blocking", action="store_true", help="e2e leg: blocking fq_solve_multi calls, one after the other")
-    ap.add_argument("--slices", type=int, default=0, help="throughput_slices option for the e2e leg (0 = library default)")
-    ap.add_argument("--safe-first", action="store_true", help="enqueue the safe launch of a step before the whole launch")
-    ap.add_argument("--single-stream", action="store_true", help="whole and safe launch of a step on one stream (serialised)")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--single-stream", action="store_true", help="all chains on one stream / context (no overlap of consecutive batches)")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: main timing only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -179,296 +256,476 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    solver = capi.Solver(local)
-    C = args.corridors
-    works = [make_workload(C, 10000 * (rank + 1), "whole"), make_workload(C, 10000 * (rank + 1) + 5000, "safe")]
-    n_cand = C * CAND
-
-    # ---- pinned host copies (e2e path) and device-resident copies (value path)
-    keys = ["x0", "xf", "lim", "poly_ofs", "face_ofs", "Ab", "cand_ofs", "dt", "sigma"]
-    host, devt, outs_h, outs_d = [], [], [], []
-    for w in works:
-        h = {k: torch.from_numpy(np.ascontiguousarray(w[k])).pin_memory() for k in keys}
-        host.append(h)
-        devt.append({k: v.to(dev) for k, v in h.items()})
-        outs_h.append((torch.zeros(n_cand, dtype=torch.uint8).pin_memory(), torch.zeros(n_cand, dtype=torch.float64).pin_memory()))
-        outs_d.append((torch.zeros(n_cand, dtype=torch.uint8, device=dev), None,
-                       torch.zeros(n_cand, dtype=torch.int32, device=dev)))
-    from faster_b200 import shard
-    cost_all = torch.zeros(2 * n_cand, dtype=torch.float64, device=dev)       # [whole costs | safe costs]
-    outs_d = [(o[0], cost_all[k * n_cand:(k + 1) * n_cand], o[2]) for k, o in enumerate(outs_d)]
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    # a dedicated (non-default) stream: its handle is what the C ABI launches on, and the timing events are
-    # recorded on the same stream (handle 0 would mean "the context's own stream" to the ABI)
-    tstream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
-
-    # hint for the device-pointer API (the host-pointer API derives it itself): sizes the per-warp row list
-    solver.set_option("max_faces_per_polytope", max(w["max_poly_faces"] for w in works))
-
-    # the whole and the safe launch of a step are independent (different inputs and outputs), so the safe one goes on
-    # a second stream forked from / joined back into the timing stream: its CTAs start on the SMs the whole launch's
-    # persistent CTAs vacate, instead of waiting for the last one to finish
-    tstream2 = torch.cuda.Stream(device=dev)
-    streams = [stream, tstream2.cuda_stream] if not args.single_stream else [stream, stream]
-    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
-
-    def step_resident(with_iters=False):
-        if not args.single_stream:
-            ev_fork.record(tstream)
-            tstream2.wait_event(ev_fork)
-        order = (1, 0) if args.safe_first else (0, 1)
-        for w, d, o, st in [(works[k], devt[k], outs_d[k], streams[k]) for k in order]:
-            solver.solve_multi_dev(w["N"], w["ff"], w["n_prob"], d["x0"].data_ptr(), d["xf"].data_ptr(),
-                                   d["lim"].data_ptr(), d["poly_ofs"].data_ptr(), d["face_ofs"].data_ptr(),
-                                   d["Ab"].data_ptr(), d["cand_ofs"].data_ptr(), CAND, w["max_faces"],
-                                   d["dt"].data_ptr(), d["sigma"].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), 0,
-                                   o[2].data_ptr() if with_iters else 0, st)
-        if not args.single_stream:
-            ev_join.record(tstream2)
-            tstream.wait_event(ev_join)
-        if world > 1:   # the path's one exchange: all-gather of the per-candidate costs (+inf = infeasible)
-            shard.all_gather_costs(cost_all, world * C, 2 * CAND)
-
-    # e2e: host buffers through the C ABI, one solver context per trajectory kind (the reference keeps two solver
-    # objects, sg_whole_ and sg_safe_).  Each batch is enqueued without waiting (fq_solve_multi_async), then both are
-    # waited for: the safe batch uploads and starts while the whole batch's last launch drains.
-    solvers_e2e = [solver, capi.Solver(local)]
-    if args.slices:
-        for sv in solvers_e2e:
-            sv.set_option("throughput_slices", args.slices)
-    e2e_np = [tuple(h[k].numpy() for k in ("x0", "xf", "lim", "poly_ofs", "face_ofs", "Ab", "cand_ofs", "dt", "sigma")) for h in host]
-    e2e_out = [(o[0].numpy(), o[1].numpy(), None, None) for o in outs_h]
-
-    def step_e2e():
-        for sv, w, a, o in zip(solvers_e2e, works, e2e_np, e2e_out):
-            sv.solve_multi(w["N"], w["ff"], *a, out=o, deferred=not args.e2e_blocking)
-        if not args.e2e_blocking:
-            for sv in solvers_e2e:
-                sv.wait()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing
+    if args.config != "cfg4":
+        line = bench_single(args, args.config, torch, capi, dev, local, world, rank, barrier, main_line=True)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- contexts: two (chains of consecutive batches overlap on two streams), each attached to the communicator
+    n_ctx = 1 if args.single_stream else 2
+    solvers = [capi.Solver(local) for _ in range(n_ctx)]
+    if world > 1:
+        for k, sv in enumerate(solvers):                     # one communicator per context: collectives of the two streams
+            uid = [capi.comm_unique_id() if rank == 0 else None]      # must not share one (NCCL orders per communicator)
+            dist.broadcast_object_list(uid, src=0)
+            sv.comm_init(uid[0], rank, world)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_ctx)]
+    tstream = torch.cuda.Stream(device=dev)                  # timing stream: forks to / joins from the chain streams
+    torch.cuda.set_stream(tstream)
+    C, ring, inner = args.corridors, args.ring, args.inner
+    n_fix = 512
+    batches = [PairBatch(load_cfg4(((rank * ring + b) * C) % n_fix, C), dev, torch, capi, gather_world=world if world > 1 else 0)
+               for b in range(ring)]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    ev_fork = torch.cuda.Event()
+    ev_join = [torch.cuda.Event() for _ in range(n_ctx)]
+
+    def run_passes(n_pass, bl):
+        ev_fork.record(tstream)
+        for s in streams:
+            s.wait_event(ev_fork)
+        for p in range(n_pass):
+            k = p % n_ctx
+            b = bl[p % len(bl)]
+            solvers[k].replan_pairs_dev(b.args, b.gathered.data_ptr() if b.gathered is not None else 0, streams[k].cuda_stream)
+        for k, s in enumerate(streams):
+            ev_join[k].record(s)
+            tstream.wait_event(ev_join[k])
+
+    def timed(n_steps, n_pass, bl):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        barrier()
+        for i in range(n_steps):
+            flush.zero_()                                    # L2 flush between timed steps (outside the events)
+            ev[i][0].record(tstream)
+            run_passes(n_pass, bl)
+            ev[i][1].record(tstream)
+        barrier()
+        return [a.elapsed_time(b) for a, b in ev]
+
     for _ in range(args.warmup):
-        step_resident()
+        run_passes(inner, batches)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for i in range(args.steps):
-        flush.zero_()                                              # L2 flush between timed steps (outside the events)
-        ev[i][0].record()
-        step_resident()
-        ev[i][1].record()
-    barrier()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
+    step_ms = timed(args.steps, inner, batches)
     total_ms = float(sum(step_ms))
-    # per-launch kernel time: time the two solve launches alone (no collective)
-    barrier()
-    kms = []
-    for i in range(min(args.steps, 10)):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for w, d, o in zip(works, devt, outs_d):
-            solver.solve_multi_dev(w["N"], w["ff"], w["n_prob"], d["x0"].data_ptr(), d["xf"].data_ptr(),
-                                   d["lim"].data_ptr(), d["poly_ofs"].data_ptr(), d["face_ofs"].data_ptr(),
-                                   d["Ab"].data_ptr(), d["cand_ofs"].data_ptr(), CAND, w["max_faces"],
-                                   d["dt"].data_ptr(), d["sigma"].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), 0, 0, stream)
-        b.record()
-        torch.cuda.synchronize()
-        kms.append(a.elapsed_time(b) / 2.0)
-    kernel_ms = float(np.mean(kms))
-    # ---- e2e timing (host buffers, copies inside)
-    for _ in range(args.warmup):
-        step_e2e()
+    res0 = batches[0].results(capi)
+
+    # ---- strong scaling: the SAME 64 corridors x 1024 pairs split over the ranks (cfg4 as written: 65 536 over 8 GPUs)
+    strong = None
+    if world > 1:
+        lo, hi = capi.shard_range(C, None, rank, world)
+        sb = [PairBatch(load_cfg4((b * C + lo) % n_fix, hi - lo), dev, torch, capi, gather_world=world) for b in range(ring)]
+        # equal shard sizes are what the all-gather needs: C is a multiple of the world sizes used (64 / 2,4,8)
+        run_passes(inner, sb)
+        sms = timed(max(3, args.steps // 2), inner, sb)
+        t = torch.tensor([float(sum(sms))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "value": C * 1024 * inner * len(sms) / (float(t.item()) * 1e-3), "unit": "pairs/s",
+                  "pairs_per_pass_total": C * 1024, "corridors_per_gpu_per_pass": hi - lo, "steps": len(sms)}
+        del sb
+
+    # ---- e2e: pinned host arrays through fq_replan_pairs_async, two contexts alternating
+    host = []
+    for b in batches[:max(2, n_ctx)]:
+        hw = dict(b.w)
+        for k in PAIR_KEYS:
+            hw[k] = torch.from_numpy(np.ascontiguousarray(b.w[k])).pin_memory().numpy()
+        n, nc = hw["n_prob"], pairs_per_pass(hw)
+        ho = dict(results=torch.zeros(n * 144, dtype=torch.uint8).pin_memory().numpy().view(capi.PAIR_RESULT_DTYPE),
+                  feasible_whole=torch.zeros(nc, dtype=torch.uint8).pin_memory().numpy(), cost_whole=torch.zeros(nc, dtype=torch.float64).pin_memory().numpy(),
+                  feasible_safe=torch.zeros(nc, dtype=torch.uint8).pin_memory().numpy(), cost_safe=torch.zeros(nc, dtype=torch.float64).pin_memory().numpy())
+        host.append((hw, ho))
+    e2e_solvers = [capi.Solver(local) for _ in range(2)]     # plain contexts: the e2e leg measures the host path of one GPU
+
+    def e2e_passes(n_pass):
+        for p in range(n_pass):
+            hw, ho = host[p % len(host)]
+            e2e_solvers[p % 2].replan_pairs(hw, deferred=True, out=ho)
+        for sv in e2e_solvers:
+            sv.wait()
+    e2e_inner = max(2, inner // 4)
+    e2e_passes(4)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step_e2e()
+        e2e_passes(e2e_inner)
     barrier()
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    # iteration statistics (one extra, untimed launch) and a sanity check that e2e and resident paths agree
-    step_resident(with_iters=True)
-    torch.cuda.synchronize()
-    iters = torch.cat([outs_d[0][2], outs_d[1][2]]).abs().double()
-    feas_frac = float(torch.cat([outs_d[0][0], outs_d[1][0]]).double().mean())
-    same = all(bool(torch.equal(outs_d[k][0].cpu(), outs_h[k][0])) for k in range(2))
+    same = bool(host[0][1]["results"].tobytes() == res0.tobytes())
+    h2d = sum(int(host[0][0][k].nbytes) for k in PAIR_KEYS)
+    d2h = sum(int(v.nbytes) for v in host[0][1].values())
 
-    # single-replan latency: one genNewTraj sweep (10 factors x all 66 monotone assignments) through the C ABI,
-    # host buffers in, winner's coefficients out -- what the robot experiences against its 10 ms budget
-    from faster_b200 import corridor as cr
-    pb = works[0]["probs"][0]
-    sig66 = cr.monotone_sigmas(N_SEG, 3)
-    dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N_SEG)
-    dts10 = np.arange(1.0, 11.0) * max(dti, 2 * pb["DC"])
-    lat = []
-    for i in range(60):
-        t0 = time.perf_counter()
-        g = solver.gen_new_traj(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts10, sig66, True)
-        lat.append(time.perf_counter() - t0)
-    replan_us = float(np.median(lat[10:]) * 1e6)
-    lat = []
-    for i in range(40):
-        t0 = time.perf_counter()
-        ge = solver.gen_new_traj_exact(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts10, True)
-        lat.append(time.perf_counter() - t0)
-    replan_exact_us = float(np.median(lat[10:]) * 1e6)
-    # the reference's SHIPPED parameters (param/faster.yaml: N_whole = 6, max_poly_whole = 3): all 3^6 = 729 assignments
-    import itertools
-    pb6 = cr.make_corridor(10000, 3, 6)
-    sig729 = np.array(list(itertools.product(range(3), repeat=6)), np.uint8)
-    dts6 = np.arange(1.0, 11.0) * max(capi.dt_initial(pb6["x0"], pb6["xf"], pb6["lim"], 6), 2 * pb6["DC"])
-    lat = []
-    for i in range(40):
-        t0 = time.perf_counter()
-        solver.gen_new_traj(6, pb6["x0"], pb6["xf"], pb6["lim"], pb6["polys"], dts6, sig729, True)
-        lat.append(time.perf_counter() - t0)
-    replan_yaml_us = float(np.median(lat[10:]) * 1e6)
-
-    # the whole replan input chain with the product's own host code: voxel map -> JPS3D -> convex decomposition ->
-    # exact sweep on the GPU (BASELINE config 4's pipeline), median over a few random forests
-    pipe = {"jps_us": [], "decomp_us": [], "sweep_exact_us": []}
-    if rank == 0:
-        for sd in range(12):
-            try:
-                _, centres, radii = cr.make_forest(3000 + sd)
-                grid_j, origin, res = cr.voxelise_forest(centres, radii, inflation=0.47)
-                grid_o, _, _ = cr.voxelise_forest(centres, radii)
-                rng = np.random.default_rng(sd)
-                s0 = np.array([rng.uniform(-6, 6), rng.uniform(-6, 6), 1.0])
-                ang = rng.uniform(-np.pi, np.pi)
-                t1 = s0 + 4.0 * np.array([np.cos(ang), np.sin(ang), 0.0])
-                t0 = time.perf_counter()
-                path, _ = capi.jps3d_plan_world(grid_j, origin, res, s0, t1, True)
-                tj = time.perf_counter() - t0
-                if len(path) < 2:
-                    continue
-                verts = cr.split_long_segments(path, 1.5)[:4]
-                obs = (np.argwhere(grid_o > 0)[:, ::-1] + 0.5) * res + origin
-                t0 = time.perf_counter()
-                polys = capi.ellipsoid_decomp(verts, obs, (2.0, 2.0, 1.0), 0.42, 0.0, cap_rows=8192)
-                td = time.perf_counter() - t0
-                x0p = np.concatenate([verts[0], np.zeros(6)]); xfp = np.concatenate([verts[-1], np.zeros(6)])
-                dtp = np.arange(1.0, 11.0) * max(capi.dt_initial(x0p, xfp, [5.0, 5.0, 8.0], N_SEG), 0.02)
-                solver.gen_new_traj_exact(N_SEG, x0p, xfp, [5.0, 5.0, 8.0], polys, dtp, True)
-                t0 = time.perf_counter()
-                solver.gen_new_traj_exact(N_SEG, x0p, xfp, [5.0, 5.0, 8.0], polys, dtp, True)
-                ts = time.perf_counter() - t0
-                pipe["jps_us"].append(tj * 1e6); pipe["decomp_us"].append(td * 1e6); pipe["sweep_exact_us"].append(ts * 1e6)
-            except Exception:
-                continue
-    pipeline = {k: (float(np.median(v)) if v else None) for k, v in pipe.items()}
-    pipeline["what"] = "random forest 16 m x 16 m x 3 m at 0.15 m (107x107x20 cells, ~7 k occupied cells), 4 m query, <= 3 polytopes"
-
-    t = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, kernel_ms = [float(x) for x in t.cpu()]
-    pairs_per_step = world * C * CAND
-    value = pairs_per_step * args.steps / (total_ms * 1e-3)
-    e2e = pairs_per_step * args.steps / e2e_s
+    total_ms, e2e_s = [float(x) for x in t.cpu()]
+    pairs_pass = world * C * 1024
+    value = pairs_pass * inner * args.steps / (total_ms * 1e-3)
+    e2e = pairs_pass * e2e_inner * args.steps / e2e_s
+
+    line = None
     if rank == 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": cfg4_config(world, C),
+                "run": {"passes_per_step": inner, "distinct_batches": ring,
+                        "streams": "one" if args.single_stream else
+                                   "two contexts / streams: the chains of consecutive batches overlap (the tail of one fills with the next)"},
+                "timed_region_s": total_ms * 1e-3,
+                "step_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)),
+                            "min": float(np.min(step_ms)), "max": float(np.max(step_ms)), "note": "rank 0's steps"},
+                "ms_per_pass": total_ms / args.steps / inner,
+                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d * e2e_inner, "d2h_bytes_per_step": d2h * e2e_inner,
+                        "passes_per_step": e2e_inner, "h2d_bytes_per_pass": h2d, "d2h_bytes_per_pass": d2h,
+                        "how": "fq_replan_pairs_async on two solver contexts + fq_wait; pinned host arrays; per-candidate flags and costs of both sweeps and the result records come back",
+                        "matches_resident": same},
+                "gpu_launches": 11 * inner * args.steps,
+                "gpu_launches_note": "per pass: 2 dt-base, 2 grid-expand, 2 sweep solves, 2 selections, 1 winners' solve, R sampling, result records",
+                "clocks": sampler.summary()}
+        if strong:
+            line["strong"] = strong
+    if args.quick:
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- the dominant kernel alone: the two sweep launches of batch 0, replicated on expanded arrays, CUDA-event timed
+    kern = sweep_kernel_times(batches[0], res0, e2e_solvers[0], torch, capi, dev, tstream, flush)
+    if rank == 0:
+        feas = np.concatenate([batches[0].out["feasible_whole"].cpu().numpy(), batches[0].out["feasible_safe"].cpu().numpy()])
+        line["config"]["feasible_fraction"] = float(feas.mean())
+        line["config"]["mean_active_set_iters"] = kern["mean_iters"]
+        line["config"]["active_set_iters_p99_max"] = kern["iters_p99_max"]
+        line["config"]["iteration_cap_hits"] = kern["cap_hits"]
+        nc = C * 1024
+        kernel_ms = 0.5 * (kern["whole_ms"] + kern["safe_ms"])
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = n_cand * BYTES_PER_CAND / (kernel_ms * 1e-3) / 1e9
-        # DRAM traffic and pipe utilisation come from the committed ncu capture of this kernel (profiles/): they cannot
-        # be measured inside an unprofiled run.  Mean of the whole and safe launches.
-        prof = {}
-        try:
-            pj = json.load(open(os.path.join(ROOT, "profiles", "kernel_metrics_latest.json")))
-            ls = [l for l in pj["launches"] if "fq_solve_kernel" in l["kernel"]]
-            prof = {"traffic": float(np.mean([l["dram_bytes"] for l in ls])),
-                    "fp64_pipe_active_pct": float(np.mean([l["fp64_pipe_active_pct"] for l in ls])),
-                    "issue_active_pct": float(np.mean([l["issue_active_pct"] for l in ls])),
-                    "warp_instructions_per_candidate": float(np.mean([l["warp_instructions"] for l in ls]) / n_cand),
-                    "source": pj["label"]}
-            if all("lsu_data_pipe_pct_of_peak" in l for l in ls):
-                # the unit this kernel loads most: the L1/shared-memory data pipe (ncu, % of peak over the elapsed launch)
-                prof["shared_memory_pipe"] = {
-                    "pct_of_peak": float(np.mean([l["lsu_data_pipe_pct_of_peak"] for l in ls])),
-                    "pct_of_peak_while_sm_active": float(np.mean([l["lsu_data_pipe_pct_of_peak_while_sm_active"] for l in ls])),
-                    "metric": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"}
-            if all("fp64_flops" in l for l in ls):
-                # executed FP64 flops per launch (ncu counters) over the live launch time, against the NOMINAL FP64 peak
-                fl = float(np.mean([l["fp64_flops"] for l in ls]))
-                prof["fp64"] = {"flops_per_launch": fl, "achieved_tflops": fl / (kernel_ms * 1e-3) / 1e12,
-                                "peak_tflops_nominal": 37.2, "frac": fl / (kernel_ms * 1e-3) / 1e12 / 37.2}
-        except Exception:
-            pass
-        h2d = sum(int(h[k].numel() * h[k].element_size()) for h in host for k in keys)
-        d2h = sum(int(o[0].numel() + 8 * o[1].numel()) for o in outs_h)
-        line = {"metric": "candidate (whole+safe pair) trajectory solves/sec", "value": value, "unit": "pairs/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "cfg2-pairs: N=10, whole P=3 + safe P=4, 1024 pairs/corridor (16 dt x 64 sigma)",
-                           "corridors_per_gpu": C, "pairs_per_step": pairs_per_step,
-                           "l2": "flushed between timed steps (256 MiB memset outside the per-step events)",
-                           "streams": "one (whole then safe)" if args.single_stream else "two (safe launch forked from / joined into the timed stream)",
-                           "parallelism": "corridor shards per rank, all-gather of costs" if world > 1 else "single GPU",
-                           "feasible_fraction": feas_frac, "mean_active_set_iters": float(iters.mean()),
-                           "active_set_iters_p99_max": [float(torch.quantile(iters[::16], 0.99)), float(iters.max())],
-                           "e2e_matches_resident": same},
-                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "how": "fq_solve_multi, blocking, whole then safe" if args.e2e_blocking else
-                               "fq_solve_multi_async on two solver contexts (whole, safe) + fq_wait; pinned host buffers"},
-                "gpu_launches": 2 * args.steps,
-                "replan_pipeline_us": pipeline,
-                "replan_latency_us": {"value": replan_us, "what": "fq_gen_new_traj: 10 factors x 66 assignments, N=10, P=3, host in/out, median of 50",
-                                      "exact_miqp": replan_exact_us, "shipped_yaml_N6_P3_all_729_assignments": replan_yaml_us, "exact_nodes": int(ge["nodes"]), "exact_same_winner": bool(ge["dt_index"] == g["dt_index"] and abs(ge["cost"] - g["cost"]) <= 1e-9 * max(1.0, g["cost"]))},
-                "clocks": sampler.summary(),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": prof.get("traffic"), "kernel": "fq_solve_kernel_t<10,*>", "kernel_ms": kernel_ms,
-                             "ncu": prof,
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
-                             "algorithmic_bytes_per_candidate": BYTES_PER_CAND,
-                             "note": "HBM fraction is tiny by construction (SURVEY 8d); the nearest hardware limit is the shared-memory data pipe (see ncu.shared_memory_pipe), then FP64 issue"}}
-        line["config"]["iteration_cap_hits"] = int((torch.cat([outs_d[0][2], outs_d[1][2]]) < 0).sum())
-        if not args.no_cpu_baseline:
-            # checker: the first corridors of this very workload re-solved by the CPU restatement
-            from oracle import pyoracle as po
-            nchk = min(C, 8)
-            mism, worst = 0, 0.0
-            for w, o in zip(works, outs_d):
-                sub = dict(w)
-                fo, co = po.solve_multi(N_SEG, w["ff"], w["x0"][:nchk], w["xf"][:nchk], w["lim"][:nchk],
-                                        w["poly_ofs"][:nchk + 1], w["face_ofs"][:w["poly_ofs"][nchk] + 1],
-                                        w["Ab"][:w["face_ofs"][w["poly_ofs"][nchk]]], w["cand_ofs"][:nchk + 1],
-                                        w["dt"][:nchk * CAND], w["sigma"][:nchk * CAND], os.cpu_count() or 1)
-                fg = o[0][:nchk * CAND].cpu().numpy()
-                cg = o[1][:nchk * CAND].cpu().numpy()
-                mism += int((fg != fo).sum())
-                ok = fo.astype(bool) & fg.astype(bool)
-                if ok.any():
-                    worst = max(worst, float((np.abs(cg[ok] - co[ok]) / np.maximum(1e-9, np.abs(co[ok]))).max()))
-            line["parity"] = {"checked_candidates": 2 * nchk * CAND, "flag_mismatches": mism, "max_rel_cost_err": worst,
-                              "against": "oracle/fq_oracle.c (CPU restatement), same inputs"}
-            threads = os.cpu_count() or 1
-            rate, sample = cpu_reference_rate(max(4, threads // 4), threads, args.cpu_seconds)
-            # the robot's view on the CPU: one sequential genNewTraj sweep with branch-and-bound over all assignments
-            lat_cpu = []
-            for _ in range(15):
-                t0 = time.perf_counter()
-                po.gen_new_traj(N_SEG, pb["x0"], pb["xf"], pb["lim"], pb["polys"], pb["DC"], 1.0, 10.0, 1.0, None, True)
-                lat_cpu.append(time.perf_counter() - t0)
-            line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample,
-                                    "replan_latency_us": float(np.median(lat_cpu) * 1e6)}
+        achieved = nc * BYTES_PER_CAND[10] / (kernel_ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "kernel": "fqt::fq_solve_kernel_t<10,*> (whole and safe sweep launches)",
+                            "kernel_ms": kernel_ms, "kernel_ms_whole": kern["whole_ms"], "kernel_ms_safe": kern["safe_ms"],
+                            "kernel_share_of_pass": (kern["whole_ms"] + kern["safe_ms"]) / (total_ms / args.steps / inner) if n_ctx == 1 else None,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                            "algorithmic_bytes_per_candidate": BYTES_PER_CAND[10],
+                            "note": "HBM fraction is tiny by construction (SURVEY 8d: 195 B and ~4 k warp instructions per candidate); "
+                                    "the nearest hardware limits are the shared-memory data pipe and issue slots: see ncu"}
+        line["roofline"].update(ncu_summary(kernel_ms))
+    # ---- parity: a slice of batch 0 against the CPU restatement of the chain, and the tolerance / margin picture
+    if rank == 0 and not args.no_cpu_baseline:
+        line["parity"] = parity_block(batches[0], res0, e2e_solvers[0], torch, capi, dev)
+    # ---- single-replan latency (what the robot experiences against its 10 ms budget)
+    if rank == 0:
+        line["replan_latency_us"] = latency_block(e2e_solvers[0], capi)
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, sample = cpu_pair_rate(max(2, min(8, threads // 8)), threads, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample}
+    if world == 1 and not args.no_other_configs:
+        line["other_configs"] = {}
+        for name in ("cfg2", "cfg3", "cfg5"):
+            try:
+                line["other_configs"][name] = bench_single(args, name, torch, capi, dev, local, world, rank, barrier, main_line=False)
+            except Exception as e:                        # a side measurement must not take the main line down
+                line["other_configs"][name] = {"error": repr(e)}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_summary(kernel_ms):
+    """DRAM traffic and pipe utilisation come from the committed ncu capture of this kernel (profiles/): they cannot be
+    measured inside an unprofiled run."""
+    try:
+        pj = json.load(open(os.path.join(ROOT, "profiles", "kernel_metrics_latest.json")))
+        ls = [l for l in pj["launches"] if "fq_solve_kernel" in l["kernel"]]
+        out = {"traffic": float(np.mean([l["dram_bytes"] for l in ls])),
+               "ncu": {"source": pj["label"], "fp64_pipe_active_pct": float(np.mean([l["fp64_pipe_active_pct"] for l in ls])),
+                       "issue_active_pct": float(np.mean([l["issue_active_pct"] for l in ls]))}}
+        if all("lsu_data_pipe_pct_of_peak" in l for l in ls):
+            out["ncu"]["shared_memory_pipe_pct_of_peak"] = float(np.mean([l["lsu_data_pipe_pct_of_peak"] for l in ls]))
+        return out
+    except Exception:
+        return {}
+
+
+def expanded_arrays(b, res, kind, torch, dev):
+    """The candidate arrays the chain builds on the device, rebuilt from the result records (dt bases, R): lets the sweep
+    launches run alone through fq_solve_multi_dev and the oracle check exactly the same candidates."""
+    w = b.w
+    n = w["n_prob"]
+    fac, sig = w["factors_" + kind], w["sigmas_" + kind]
+    base = res["whole_dt_base" if kind == "whole" else "safe_dt_base"]
+    dts = (base[:, None, None] * fac[None, :, None] * np.ones((1, 1, len(sig)))).reshape(-1)
+    sg = np.ascontiguousarray(np.broadcast_to(sig[None, None], (n, len(fac), len(sig), sig.shape[1])).reshape(-1, sig.shape[1]))
+    co = (np.arange(n + 1) * len(fac) * len(sig)).astype(np.int32)
+    x0 = w["x0"] if kind == "whole" else np.ascontiguousarray(res["R"])
+    return dict(x0=x0, xf=w["xf_" + kind], dt=np.ascontiguousarray(dts), sigma=sg, cand_ofs=co)
+
+
+def sweep_kernel_times(b, res, solver, torch, capi, dev, tstream, flush):
+    out = {}
+    iters_all = []
+    for kind, N, ff in (("whole", b.w["N_whole"], True), ("safe", b.w["N_safe"], False)):
+        e = expanded_arrays(b, res, kind, torch, dev)
+        d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in e.items()}
+        nc = len(e["dt"])
+        feas = torch.zeros(nc, dtype=torch.uint8, device=dev); cost = torch.zeros(nc, dtype=torch.float64, device=dev)
+        its = torch.zeros(nc, dtype=torch.int32, device=dev)
+        solver.set_option("max_faces_per_polytope", b.w["max_poly_faces_" + kind])
+
+        def launch(with_iters):
+            solver.solve_multi_dev(N, ff, b.w["n_prob"], d["x0"].data_ptr(), d["xf"].data_ptr(), b.d["lim"].data_ptr(),
+                                   b.d["poly_ofs_" + kind].data_ptr(), b.d["face_ofs_" + kind].data_ptr(), b.d["Ab_" + kind].data_ptr(),
+                                   d["cand_ofs"].data_ptr(), nc // b.w["n_prob"], b.w["max_faces_" + kind], d["dt"].data_ptr(),
+                                   d["sigma"].data_ptr(), feas.data_ptr(), cost.data_ptr(), 0, its.data_ptr() if with_iters else 0,
+                                   tstream.cuda_stream)
+        launch(False)
+        ms = []
+        for _ in range(10):
+            flush.zero_()
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(tstream); launch(False); z.record(tstream)
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(z))
+        out[kind + "_ms"] = float(np.mean(ms))
+        launch(True)
+        torch.cuda.synchronize()
+        assert bool(torch.equal(feas, b.out["feasible_" + kind])), "replicated %s sweep differs from the chain's" % kind
+        iters_all.append(its.cpu().numpy())
+    solver.set_option("max_faces_per_polytope", 0)
+    it = np.concatenate(iters_all)
+    out["cap_hits"] = int((it < 0).sum())
+    it = np.abs(it).astype(float)
+    out["mean_iters"] = float(it.mean())
+    out["iters_p99_max"] = [float(np.percentile(it, 99)), float(it.max())]
+    return out
+
+
+def parity_block(b, res, solver, torch, capi, dev, n_chk=4):
+    """Oracle check of the first corridors of batch 0, plus what the row tolerance does to the flags."""
+    from oracle import pair_oracle, pyoracle as po
+    w = load_cfg4_like(b.w, n_chk)
+    g = solver.replan_pairs(w)
+    r = g["results"]
+    o = pair_oracle.replan_pairs(w, os.cpu_count() or 1, dt_base_whole=r["whole_dt_base"], dt_base_safe=r["safe_dt_base"])
+    mism = int((g["feasible_whole"] != o["feasible_whole"]).sum() + (g["feasible_safe"] != o["feasible_safe"]).sum())
+    worst = 0.0
+    for k in ("whole", "safe"):
+        ok = o["feasible_" + k].astype(bool) & g["feasible_" + k].astype(bool)
+        if ok.any():
+            worst = max(worst, float((np.abs(g["cost_" + k][ok] - o["cost_" + k][ok]) / np.maximum(1e-9, np.abs(o["cost_" + k][ok]))).max()))
+    out = {"checked_candidates": int(2 * pairs_per_pass(w)), "flag_mismatches": mism, "max_rel_cost_err": worst,
+           "winner_mismatches": int((r["whole_dt_index"] != o["whole_dt_index"]).sum() + (r["whole_sigma_index"] != o["whole_sigma_index"]).sum() +
+                                    (r["safe_dt_index"] != o["safe_dt_index"]).sum() + (r["safe_sigma_index"] != o["safe_sigma_index"]).sum()),
+           "dt_base_mismatches_device_vs_cpu": int((r["whole_dt_base"] != o["whole_dt_base_own"]).sum()),
+           "against": "oracle/ (CPU restatement of the chain), same inputs"}
+    # tolerance regime: Gurobi's default FeasibilityTol is 1e-6 (the reference sets none, solverGurobi.cpp:479-487); ours 1e-8
+    full = b.w
+    base = solver.replan_pairs(full, want_coeffs=False)
+    solver.set_option("row_tol_1e9", 1000)
+    loose = solver.replan_pairs(full, want_coeffs=False)
+    solver.set_option("row_tol_1e9", 10)
+    flips = {k: int((base["feasible_" + k] != loose["feasible_" + k]).sum()) for k in ("whole", "safe")}
+    out["flag_flips_tol_1e-6_vs_1e-8"] = {"whole": flips["whole"], "safe": flips["safe"], "of": int(pairs_per_pass(full)),
+                                          "winner_changes": int((base["results"]["whole_dt_index"] != loose["results"]["whole_dt_index"]).sum() +
+                                                                (base["results"]["safe_dt_index"] != loose["results"]["safe_dt_index"]).sum())}
+    # feasibility margins: flags with every polytope offset b and every limit moved by s (s < 0 tightens).  A candidate
+    # whose flag differs between -s and +s lies within s of the feasibility boundary.
+    hist = {}
+    for s in (1e-6, 1e-5, 1e-4, 1e-3):
+        fl = []
+        for sign in (-1.0, 1.0):
+            ws = dict(full)
+            for k in ("whole", "safe"):
+                A = full["Ab_" + k].copy(); A[:, 3] += sign * s; ws["Ab_" + k] = A
+            ws["lim"] = full["lim"] + sign * s
+            fl.append(solver.replan_pairs(ws, want_coeffs=False))
+        hist["within_%g" % s] = {k: int((fl[0]["feasible_" + k] != fl[1]["feasible_" + k]).sum()) for k in ("whole", "safe")}
+    out["feasibility_margin_counts"] = hist
+    out["feasibility_margin_note"] = "candidates whose flag changes when every row bound moves by -s vs +s (m, m/s, m/s2, m/s3); safe counts include the effect on R"
+    return out
+
+
+def load_cfg4_like(w, n):
+    """First n corridors of a pair workload dict."""
+    out = dict(w)
+    out["n_prob"] = n
+    for k in ("x0", "xf_whole", "xf_safe", "lim"):
+        out[k] = np.ascontiguousarray(w[k][:n])
+    for kind in ("whole", "safe"):
+        po, fo = w["poly_ofs_" + kind], w["face_ofs_" + kind]
+        out["poly_ofs_" + kind] = np.ascontiguousarray(po[:n + 1])
+        out["face_ofs_" + kind] = np.ascontiguousarray(fo[:po[n] + 1])
+        out["Ab_" + kind] = np.ascontiguousarray(w["Ab_" + kind][:fo[po[n]]])
+    return out
+
+
+def latency_block(solver, capi):
+    from faster_b200 import corridor as cr
+    w = load_cfg4(0, 1)
+    polys = [(w["Ab_whole"][w["face_ofs_whole"][p]:w["face_ofs_whole"][p + 1], :3], w["Ab_whole"][w["face_ofs_whole"][p]:w["face_ofs_whole"][p + 1], 3])
+             for p in range(3)]
+    x0, xf, lim = w["x0"][0], w["xf_whole"][0], w["lim"][0]
+    sig66 = cr.monotone_sigmas(N_SEG, 3)
+    dts10 = np.arange(1.0, 11.0) * max(capi.dt_initial(x0, xf, lim, N_SEG), 0.02)
+
+    def med(fn, n=50, skip=10):
+        lat = []
+        for _ in range(n):
+            t0 = time.perf_counter(); r = fn(); lat.append(time.perf_counter() - t0)
+        return float(np.median(lat[skip:]) * 1e6), r
+    us, g = med(lambda: solver.gen_new_traj(N_SEG, x0, xf, lim, polys, dts10, sig66, True))
+    us_x, ge = med(lambda: solver.gen_new_traj_exact(N_SEG, x0, xf, lim, polys, dts10, True), 40)
+    w1 = load_cfg4(0, 1)
+    us_pair, _ = med(lambda: solver.replan_pairs(w1, want_candidates=False), 40)
+    import itertools
+    pb6 = cr.make_corridor(10000, 3, 6)
+    sig729 = np.array(list(itertools.product(range(3), repeat=6)), np.uint8)
+    dts6 = np.arange(1.0, 11.0) * max(capi.dt_initial(pb6["x0"], pb6["xf"], pb6["lim"], 6), 2 * pb6["DC"])
+    us6, _ = med(lambda: solver.gen_new_traj(6, pb6["x0"], pb6["xf"], pb6["lim"], pb6["polys"], dts6, sig729, True), 40)
+    out = {"value": us, "what": "fq_gen_new_traj: 10 factors x 66 assignments, N=10, P=3 (a cfg4 forest corridor), host in/out, median",
+           "exact_miqp": us_x, "exact_nodes": int(ge["nodes"]),
+           "exact_same_winner": bool(ge["dt_index"] == g["dt_index"] and abs(ge["cost"] - g["cost"]) <= 1e-9 * max(1.0, g["cost"])),
+           "chained_pair_one_corridor": us_pair, "chained_pair_what": "fq_replan_pairs, 1 corridor: whole 16x64 -> R -> safe 16x64, winners' coefficients back",
+           "shipped_yaml_N6_P3_all_729_assignments": us6}
+    try:
+        from oracle import pyoracle as po
+        lat = []
+        for _ in range(15):
+            t0 = time.perf_counter()
+            po.gen_new_traj(N_SEG, x0, xf, lim, polys, 0.01, 1.0, 10.0, 1.0, None, True)
+            lat.append(time.perf_counter() - t0)
+        out["cpu_restatement_exact_sweep"] = float(np.median(lat) * 1e6)
+    except Exception:
+        pass
+    return out
+
+
+def bench_single(args, name, torch, capi, dev, local, world, rank, barrier, main_line):
+    """BASELINE configs 2 / 3 / 5: one kind of candidates, resident arrays, fq_solve_multi_dev."""
+    cfg = SINGLE[name]
+    C = cfg["corridors"]
+    w = make_single(cfg, C, capi.dt_initial)
+    keys = ["x0", "xf", "lim", "poly_ofs", "face_ofs", "Ab", "cand_ofs", "dt", "sigma"]
+    d = {k: torch.from_numpy(np.ascontiguousarray(w[k])).to(dev) for k in keys}
+    nc = C * w["cand"]
+    feas = torch.zeros(nc, dtype=torch.uint8, device=dev); cost = torch.zeros(nc, dtype=torch.float64, device=dev)
+    its = torch.zeros(nc, dtype=torch.int32, device=dev)
+    solver = capi.Solver(local)
+    solver.set_option("max_faces_per_polytope", w["max_poly_faces"])
+    st = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(st)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def launch(n_prob=C, with_iters=False):
+        solver.solve_multi_dev(w["N"], w["ff"], n_prob, d["x0"].data_ptr(), d["xf"].data_ptr(), d["lim"].data_ptr(),
+                               d["poly_ofs"].data_ptr(), d["face_ofs"].data_ptr(), d["Ab"].data_ptr(), d["cand_ofs"].data_ptr(),
+                               w["cand"], w["max_faces"], d["dt"].data_ptr(), d["sigma"].data_ptr(), feas.data_ptr(), cost.data_ptr(), 0,
+                               its.data_ptr() if with_iters else 0, st.cuda_stream)
+    per_launch_ms = None
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st); launch(); z.record(st); torch.cuda.synchronize()
+    per_launch_ms = a.elapsed_time(z)
+    inner = max(1, min(64, int(round((60.0 if main_line else 25.0) / max(per_launch_ms, 0.05)))))
+    steps = args.steps if main_line else max(5, min(args.steps, 10))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record(st)
+        for _ in range(inner):
+            launch()
+        ev[i][1].record(st)
+    barrier()
+    sms = [x.elapsed_time(y) for x, y in ev]
+    total_ms = float(sum(sms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    # single launches, L2 flushed: the kernel's own time; and the literal one-corridor batch of BASELINE
+    kms, lit = [], []
+    for _ in range(8):
+        flush.zero_()
+        a.record(st); launch(); z.record(st); torch.cuda.synchronize()
+        kms.append(a.elapsed_time(z))
+        a.record(st); launch(1); z.record(st); torch.cuda.synchronize()
+        lit.append(a.elapsed_time(z))
+    launch(with_iters=True)
+    torch.cuda.synchronize()
+    it = its.cpu().numpy()
+    kernel_ms = float(np.mean(kms))
+    value = world * nc * inner * steps / (total_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bpc = BYTES_PER_CAND[w["N"]]
+    achieved = nc * bpc / (kernel_ms * 1e-3) / 1e9
+    out = {"metric": "candidate trajectory solves/sec (single kind)", "value": value, "unit": "candidates/s", "n_gpus": world,
+           "steps": steps, "warmup": 3, "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": cfg["name"], "corridors_per_gpu": C, "candidates_per_launch": nc, "launches_per_step": inner,
+                      "l2": "flushed between timed steps", "feasible_fraction": float(feas.cpu().numpy().mean()),
+                      "mean_active_set_iters": float(np.abs(it).mean()), "iteration_cap_hits": int((it < 0).sum())},
+           "timed_region_s": total_ms * 1e-3, "gpu_launches": inner * steps,
+           "literal_batch": {"what": "ONE corridor, %d candidates, one launch (BASELINE's batch as written): launch-latency bound" % w["cand"],
+                             "ms": float(np.mean(lit)), "candidates_per_s": w["cand"] / (float(np.mean(lit)) * 1e-3)},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "kernel": "fqt::fq_solve_kernel_t<%d,%d>" % (w["N"], 1 if w["ff"] else 0), "kernel_ms": kernel_ms,
+                        "algorithmic_bytes_per_candidate": bpc, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+        nchk = 1 if w["cand"] > 4096 else min(C, 4)
+        ncand = nchk * w["cand"]
+        sel = slice(0, ncand) if ncand <= 16384 else np.arange(0, ncand, ncand // 16384)
+        fo, co = po.solve_multi(w["N"], w["ff"], w["x0"][:nchk], w["xf"][:nchk], w["lim"][:nchk], w["poly_ofs"][:nchk + 1],
+                                w["face_ofs"][:w["poly_ofs"][nchk] + 1], w["Ab"][:w["face_ofs"][w["poly_ofs"][nchk]]],
+                                w["cand_ofs"][:nchk + 1], w["dt"][:ncand], w["sigma"][:ncand], os.cpu_count() or 1)
+        fg = feas[:ncand].cpu().numpy(); cg = cost[:ncand].cpu().numpy()
+        ok = fo.astype(bool) & fg.astype(bool)
+        out["parity"] = {"checked_candidates": int(ncand), "flag_mismatches": int((fg != fo).sum()),
+                         "max_rel_cost_err": float((np.abs(cg[ok] - co[ok]) / np.maximum(1e-9, np.abs(co[ok]))).max()) if ok.any() else 0.0,
+                         "against": "oracle/fq_oracle.c, same inputs"}
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < (2.0 if not main_line else args.cpu_seconds):
+            po.solve_multi(w["N"], w["ff"], w["x0"][:1], w["xf"][:1], w["lim"][:1], w["poly_ofs"][:2], w["face_ofs"][:w["poly_ofs"][1] + 1],
+                           w["Ab"][:w["face_ofs"][w["poly_ofs"][1]]], w["cand_ofs"][:2], w["dt"][:w["cand"]], w["sigma"][:w["cand"]],
+                           os.cpu_count() or 1)
+            reps += 1
+        out["cpu_baseline"] = {"value": reps * w["cand"] / (time.perf_counter() - t0), "unit": "candidates/s", "cores": os.cpu_count() or 1,
+                               "kind": "port", "sample": "1 corridor x %d candidates, %d passes" % (w["cand"], reps)}
+    solver.close()
+    return out
 
 
 if __name__ == "__main__":

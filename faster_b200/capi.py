@@ -12,11 +12,43 @@ _lib = None
 
 EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_set_option", "fq_solve_batch", "fq_solve_multi",
            "fq_solve_multi_async", "fq_wait", "fq_solve_multi_dev", "fq_gen_new_traj", "fq_gen_new_traj_sampled", "fq_gen_new_traj_exact", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
-           "fq_monotone_sigmas", "fq_plan_tables", "fq_ellipsoid_decomp", "fq_jps3d_plan", "fq_jps3d_plan_world", "fq_jps3d_rules"]
+           "fq_monotone_sigmas", "fq_plan_tables", "fq_ellipsoid_decomp", "fq_jps3d_plan", "fq_jps3d_plan_world", "fq_jps3d_rules",
+           "fq_replan_pairs", "fq_replan_pairs_async", "fq_replan_pairs_dev", "fq_create_multi", "fq_comm_unique_id", "fq_comm_init",
+           "fq_comm_info", "fq_allgather_dev", "fq_shard_range", "fq_solve_multi_sharded"]
 
 
 class FqError(RuntimeError):
     pass
+
+
+class PairResult(C.Structure):
+    """fq_pair_result of include/faster_b200.h (144 bytes)."""
+    _fields_ = [("whole_dt_index", C.c_int), ("whole_sigma_index", C.c_int), ("safe_dt_index", C.c_int),
+                ("safe_sigma_index", C.c_int), ("whole_cost", C.c_double), ("safe_cost", C.c_double),
+                ("whole_dt", C.c_double), ("safe_dt", C.c_double), ("whole_dt_base", C.c_double),
+                ("safe_dt_base", C.c_double), ("n_samples_whole", C.c_int), ("k_safe", C.c_int), ("R", C.c_double * 9)]
+
+
+PAIR_RESULT_DTYPE = np.dtype([("whole_dt_index", np.int32), ("whole_sigma_index", np.int32), ("safe_dt_index", np.int32),
+                              ("safe_sigma_index", np.int32), ("whole_cost", np.float64), ("safe_cost", np.float64),
+                              ("whole_dt", np.float64), ("safe_dt", np.float64), ("whole_dt_base", np.float64),
+                              ("safe_dt_base", np.float64), ("n_samples_whole", np.int32), ("k_safe", np.int32),
+                              ("R", np.float64, (9,))])
+assert PAIR_RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 144
+
+
+class PairArgs(C.Structure):
+    """fq_pair_args of include/faster_b200.h; pointers as integers (host or device addresses)."""
+    _fields_ = [("n_prob", C.c_int), ("N_whole", C.c_int), ("N_safe", C.c_int), ("DC", C.c_double), ("r_fraction", C.c_double),
+                ("x0", C.c_void_p), ("xf_whole", C.c_void_p), ("xf_safe", C.c_void_p), ("lim", C.c_void_p),
+                ("poly_ofs_whole", C.c_void_p), ("face_ofs_whole", C.c_void_p), ("Ab_whole", C.c_void_p),
+                ("poly_ofs_safe", C.c_void_p), ("face_ofs_safe", C.c_void_p), ("Ab_safe", C.c_void_p),
+                ("n_fac_whole", C.c_int), ("factors_whole", C.c_void_p), ("n_sig_whole", C.c_int), ("sigmas_whole", C.c_void_p),
+                ("n_fac_safe", C.c_int), ("factors_safe", C.c_void_p), ("n_sig_safe", C.c_int), ("sigmas_safe", C.c_void_p),
+                ("feasible_whole", C.c_void_p), ("cost_whole", C.c_void_p), ("feasible_safe", C.c_void_p), ("cost_safe", C.c_void_p),
+                ("coeffs_whole", C.c_void_p), ("coeffs_safe", C.c_void_p), ("results", C.c_void_p),
+                ("max_faces_whole", C.c_int), ("max_poly_faces_whole", C.c_int), ("max_faces_safe", C.c_int),
+                ("max_poly_faces_safe", C.c_int)]
 
 
 def lib():
@@ -55,6 +87,16 @@ def lib():
         L.fq_gen_new_traj_sampled.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + \
                                              [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                               C.c_double, C.c_int] + [C.c_void_p] * 6
+        L.fq_replan_pairs.argtypes = [C.c_void_p, C.POINTER(PairArgs)]
+        L.fq_replan_pairs_async.argtypes = [C.c_void_p, C.POINTER(PairArgs)]
+        L.fq_replan_pairs_dev.argtypes = [C.c_void_p, C.POINTER(PairArgs), C.c_void_p, C.c_void_p]
+        L.fq_create_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+        L.fq_comm_unique_id.argtypes = [C.c_void_p]
+        L.fq_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.fq_comm_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fq_allgather_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+        L.fq_shard_range.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.fq_solve_multi_sharded.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 13
         _lib = L
     return _lib
 
@@ -182,16 +224,145 @@ def plan_tables(N, force_final):
     return TZ, T0, FT
 
 
-class Solver:
-    """Owns an fq_ctx on one GPU."""
+def shard_range(n_prob, cand_ofs, rank, world):
+    """fq_shard_range -> (lo, hi): the problems of `rank`."""
+    lo, hi = C.c_int(0), C.c_int(0)
+    co = None if cand_ofs is None else np.ascontiguousarray(cand_ofs, np.int32)
+    rc = lib().fq_shard_range(int(n_prob), co.ctypes.data if co is not None else None, int(rank), int(world),
+                              C.addressof(lo), C.addressof(hi))
+    if rc != 0:
+        raise FqError("fq_shard_range: bad arguments")
+    return lo.value, hi.value
 
-    def __init__(self, device=0):
+
+def comm_unique_id():
+    """128-byte NCCL id (rank 0 creates it, the launcher distributes it)."""
+    buf = (C.c_char * 128)()
+    rc = lib().fq_comm_unique_id(C.addressof(buf))
+    if rc != 0:
+        raise FqError("fq_comm_unique_id failed (%d): %s" % (rc, lib().fq_last_error(None).decode()))
+    return bytes(buf)
+
+
+def make_pair_workload(whole, safe, factors_whole, sigmas_whole, factors_safe, sigmas_safe, DC=0.01, r_fraction=0.6):
+    """Packs two lists of corridor dicts (corridor.make_* output; whole[j] and safe[j] belong to one replan) into the
+    host arrays of fq_pair_args.  -> dict of numpy arrays + sizes."""
+    n = len(whole)
+    assert len(safe) == n
+
+    def csr(probs):
+        po, fo, rows = [0], [0], []
+        for pb in probs:
+            for A, b in pb["polys"]:
+                rows.append(np.hstack([np.asarray(A, float).reshape(-1, 3), np.asarray(b, float).reshape(-1, 1)]))
+                fo.append(fo[-1] + len(b))
+            po.append(po[-1] + len(pb["polys"]))
+        Ab = np.ascontiguousarray(np.vstack(rows)) if rows else np.zeros((1, 4))
+        fo = np.asarray(fo, np.int32)
+        po = np.asarray(po, np.int32)
+        mf = int(max(fo[po[j + 1]] - fo[po[j]] for j in range(len(probs)))) if rows else 1
+        mpf = int(np.diff(fo).max()) if len(fo) > 1 else 0
+        return po, fo, Ab, mf, mpf
+    pw, fw, Aw, mfw, mpfw = csr(whole)
+    ps, fs, As, mfs, mpfs = csr(safe)
+    Nw, Ns = whole[0]["N"], safe[0]["N"]
+    sw = np.ascontiguousarray(np.asarray(sigmas_whole, np.uint8).reshape(-1, Nw))
+    ss = np.ascontiguousarray(np.asarray(sigmas_safe, np.uint8).reshape(-1, Ns))
+    return dict(n_prob=n, N_whole=Nw, N_safe=Ns, DC=float(DC), r_fraction=float(r_fraction),
+                x0=np.ascontiguousarray([pb["x0"] for pb in whole], np.float64),
+                xf_whole=np.ascontiguousarray([pb["xf"] for pb in whole], np.float64),
+                xf_safe=np.ascontiguousarray([pb["xf"] for pb in safe], np.float64),
+                lim=np.ascontiguousarray([pb["lim"] for pb in whole], np.float64),
+                poly_ofs_whole=pw, face_ofs_whole=fw, Ab_whole=Aw, poly_ofs_safe=ps, face_ofs_safe=fs, Ab_safe=As,
+                factors_whole=_f64(factors_whole), sigmas_whole=sw, factors_safe=_f64(factors_safe), sigmas_safe=ss,
+                max_faces_whole=mfw, max_poly_faces_whole=mpfw, max_faces_safe=mfs, max_poly_faces_safe=mpfs)
+
+
+PAIR_INPUT_KEYS = ["x0", "xf_whole", "xf_safe", "lim", "poly_ofs_whole", "face_ofs_whole", "Ab_whole", "poly_ofs_safe",
+                   "face_ofs_safe", "Ab_safe", "factors_whole", "sigmas_whole", "factors_safe", "sigmas_safe"]
+
+
+def pair_args(w, ptr, out_ptrs):
+    """PairArgs from a make_pair_workload dict; ptr(key) -> address of input array `key`, out_ptrs: dict of output
+    addresses (feasible_whole, cost_whole, feasible_safe, cost_safe, coeffs_whole, coeffs_safe, results; 0/None = NULL)."""
+    a = PairArgs()
+    a.n_prob, a.N_whole, a.N_safe, a.DC, a.r_fraction = w["n_prob"], w["N_whole"], w["N_safe"], w["DC"], w["r_fraction"]
+    for k in PAIR_INPUT_KEYS:
+        setattr(a, k, ptr(k))
+    a.n_fac_whole, a.n_sig_whole = len(w["factors_whole"]), len(w["sigmas_whole"])
+    a.n_fac_safe, a.n_sig_safe = len(w["factors_safe"]), len(w["sigmas_safe"])
+    for k in ("feasible_whole", "cost_whole", "feasible_safe", "cost_safe", "coeffs_whole", "coeffs_safe", "results"):
+        setattr(a, k, out_ptrs.get(k) or None)
+    for k in ("max_faces_whole", "max_poly_faces_whole", "max_faces_safe", "max_poly_faces_safe"):
+        setattr(a, k, int(w[k]))
+    return a
+
+
+class Solver:
+    """Owns an fq_ctx on one GPU (or, with n_gpus > 1, a single-process multi-GPU group: fq_create_multi)."""
+
+    def __init__(self, device=0, n_gpus=1, devices=None):
         self._L = lib()
         h = C.c_void_p()
-        rc = self._L.fq_create(C.byref(h), int(device))
+        if n_gpus > 1 or devices is not None:
+            dv = None if devices is None else np.ascontiguousarray(devices, np.int32)
+            n = n_gpus if devices is None else len(dv)
+            rc = self._L.fq_create_multi(C.byref(h), int(n), dv.ctypes.data if dv is not None else None)
+        else:
+            rc = self._L.fq_create(C.byref(h), int(device))
         if rc != 0:
             raise FqError("fq_create failed (%d): %s" % (rc, self._L.fq_last_error(None).decode()))
         self._h = h
+
+    def comm_init(self, id128, rank, world):
+        """Attach this (single-GPU) context to a communicator: one process per GPU."""
+        buf = C.create_string_buffer(bytes(id128), 128)
+        self._check(self._L.fq_comm_init(self._h, C.addressof(buf), int(rank), int(world)))
+
+    def comm_info(self):
+        r, w, v = C.c_int(0), C.c_int(1), C.c_int(0)
+        self._check(self._L.fq_comm_info(self._h, C.addressof(r), C.addressof(w), C.addressof(v)))
+        return r.value, w.value, v.value
+
+    def allgather_dev(self, d_send, d_recv, nbytes, stream=0):
+        self._check(self._L.fq_allgather_dev(self._h, d_send, d_recv, int(nbytes), stream or None))
+
+    def replan_pairs(self, w, want_candidates=True, want_coeffs=True, deferred=False, out=None):
+        """fq_replan_pairs on a make_pair_workload dict (host arrays).  -> dict(results (structured array), feasible_whole,
+        cost_whole, feasible_safe, cost_safe, coeffs_whole, coeffs_safe).  deferred: valid after wait(); `out` reuses a
+        previous return value's arrays (keep it and `w` alive until then)."""
+        n = w["n_prob"]
+        ncw = n * len(w["factors_whole"]) * len(w["sigmas_whole"])
+        ncs = n * len(w["factors_safe"]) * len(w["sigmas_safe"])
+        if out is None:
+            out = dict(results=np.zeros(n, PAIR_RESULT_DTYPE))
+            if want_candidates:
+                out.update(feasible_whole=np.zeros(ncw, np.uint8), cost_whole=np.zeros(ncw), feasible_safe=np.zeros(ncs, np.uint8),
+                           cost_safe=np.zeros(ncs))
+            if want_coeffs:
+                out.update(coeffs_whole=np.zeros((n, w["N_whole"], 12)), coeffs_safe=np.zeros((n, w["N_safe"], 12)))
+        a = pair_args(w, lambda k: w[k].ctypes.data, {k: v.ctypes.data for k, v in out.items()})
+        fn = self._L.fq_replan_pairs_async if deferred else self._L.fq_replan_pairs
+        self._check(fn(self._h, C.byref(a)))
+        return out
+
+    def replan_pairs_dev(self, a, results_all=0, stream=0):
+        """fq_replan_pairs_dev: `a` is a PairArgs holding device addresses."""
+        self._check(self._L.fq_replan_pairs_dev(self._h, C.byref(a), results_all or None, stream or None))
+
+    def solve_multi_sharded(self, N, force_final, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dts, sigmas):
+        """-> (feasible, cost, win_idx, win_cost); see fq_solve_multi_sharded."""
+        n_prob = len(cand_ofs) - 1
+        n = int(cand_ofs[-1])
+        feas = np.zeros(n, np.uint8)
+        cost = np.full(n, np.nan)
+        wi = np.zeros(n_prob, np.int32)
+        wc = np.zeros(n_prob)
+        self._check(self._L.fq_solve_multi_sharded(self._h, int(N), int(bool(force_final)), n_prob, x0.ctypes.data, xf.ctypes.data,
+                                                   lim.ctypes.data, poly_ofs.ctypes.data, face_ofs.ctypes.data, Ab.ctypes.data,
+                                                   cand_ofs.ctypes.data, dts.ctypes.data, sigmas.ctypes.data, feas.ctypes.data,
+                                                   cost.ctypes.data, wi.ctypes.data, wc.ctypes.data))
+        return feas, cost, wi, wc
 
     def close(self):
         if getattr(self, "_h", None):

@@ -235,3 +235,79 @@ def make_jps_forest_corridor(seed, P, N, force_final=True, DC=0.01, n_trees=60):
     xf[:3] = verts[-1]
     return dict(N=N, P=P, x0=x0, xf=xf, lim=np.array(prof["lim"]), polys=polys, force_final=bool(force_final), DC=DC,
                 verts=verts, obs=obs, seed=seed, profile="uav", jps_path=path)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE config 4: one replan() = a whole problem and the safe problem that branches off it (faster.cpp:406-430,
+# :474-475, :485-499, :521-524).  The safe corridor depends on R, a sample of the whole SOLUTION, so it is built in two
+# steps: make_forest_pair_whole -> (solve the whole sweep, read R) -> make_forest_pair_safe.
+# ------------------------------------------------------------------------------------------------------------------
+def make_forest_pair_whole(seed, N=10, P_whole=3, n_trees=60, query=(5.5, 7.0), DC=0.01):
+    """Whole problem of one replan in a random forest: JPS path (product host code) of `query` metres, vertices at most
+    1.5 m apart (createMoreVertexes), the first P_whole segments decomposed against the occupied cells.  Keeps the whole
+    vertex list and the obstacle cloud for the safe step."""
+    from . import capi
+    prof = UAV
+    rng = np.random.default_rng(seed)
+    _, centres, radii = make_forest(seed, n_trees=n_trees)
+    grid_jps, origin, res = voxelise_forest(centres, radii, inflation=0.47)
+    grid, _, _ = voxelise_forest(centres, radii)
+    for _ in range(400):
+        s = np.array([rng.uniform(-6, 6), rng.uniform(-6, 6), rng.uniform(0.8, 1.4)])
+        ang = rng.uniform(-np.pi, np.pi)
+        t = s + rng.uniform(*query) * np.array([np.cos(ang), np.sin(ang), 0.0])
+        t[2] = rng.uniform(0.8, 1.4)
+        if np.abs(t[:2]).max() > 7.5:
+            continue
+        path, _ = capi.jps3d_plan_world(grid_jps, origin, res, s, t, True)
+        if len(path) < 2:
+            continue
+        verts_all = split_long_segments(path, 1.5)
+        if len(verts_all) >= P_whole + 2:
+            break
+    else:
+        raise RuntimeError("no path found")
+    verts = verts_all[:P_whole + 1]
+    obs = (np.argwhere(grid > 0)[:, ::-1] + 0.5) * res + origin
+    polys = capi.ellipsoid_decomp(verts, obs, prof["bbox"], prof["drone_radius"], prof["z_ground"], cap_rows=8192)
+    d0 = verts[1] - verts[0]
+    d0 /= np.linalg.norm(d0)
+    x0 = np.zeros(9)
+    x0[:3] = verts[0]
+    x0[3:6] = d0 * rng.uniform(*prof["v0"])
+    xf = np.zeros(9)
+    xf[:3] = verts[-1]
+    return dict(N=N, P=P_whole, x0=x0, xf=xf, lim=np.array(prof["lim"]), polys=polys, force_final=True, DC=DC, verts=verts,
+                verts_all=verts_all, obs=obs, seed=seed, profile="uav")
+
+
+def make_forest_pair_safe(whole, R, N=10, P_safe=4):
+    """Safe problem of the replan whose whole problem is `whole`, branching off at the state R (9: pos vel accel):
+    JPS_safe = the path ahead of R with its first vertex replaced by R.pos (faster.cpp:485), exactly P_safe segments
+    (deleteVertexes, faster.cpp:495, or an extra vertex on the longest segment when the path is short), decomposed
+    against the same cloud (no unknown space in the synthetic forest, faster.cpp:499); x0 = R, xf = M = the last vertex
+    at rest, final position free (faster.cpp:521-524)."""
+    from . import capi
+    prof = UAV
+    R = np.asarray(R, float)
+    va = whole["verts_all"]
+    best, bi = np.inf, 0
+    for i in range(len(va) - 1):                               # segment of the path closest to R
+        ab = va[i + 1] - va[i]
+        t = np.clip(((R[:3] - va[i]) @ ab) / max(ab @ ab, 1e-12), 0.0, 1.0)
+        d = np.linalg.norm(va[i] + t * ab - R[:3])
+        if d < best:
+            best, bi = d, i
+    path = [R[:3].copy()] + [v for v in va[bi + 1:]]
+    if len(path) >= 3 and np.linalg.norm(path[1] - path[0]) < 0.3:
+        del path[1]
+    path = path[:P_safe + 1]
+    while len(path) < P_safe + 1:
+        k = int(np.argmax([np.linalg.norm(path[i + 1] - path[i]) for i in range(len(path) - 1)]))
+        path.insert(k + 1, 0.5 * (path[k] + path[k + 1]))
+    path = np.array(path)
+    polys = capi.ellipsoid_decomp(path, whole["obs"], prof["bbox"], prof["drone_radius"], prof["z_ground"], cap_rows=8192)
+    xf = np.zeros(9)
+    xf[:3] = path[-1]
+    return dict(N=N, P=P_safe, x0=R[:9].copy(), xf=xf, lim=whole["lim"].copy(), polys=polys, force_final=False, DC=whole["DC"],
+                verts=path, seed=whole["seed"], profile="uav")

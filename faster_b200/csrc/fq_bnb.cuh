@@ -96,15 +96,17 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
     const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
     double2* dst = reinterpret_cast<double2*>(sAb);
     int bad = 0;
-    for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x)
+    const bool fits = nf >= 0 && nf <= a.max_faces;      // never overrun the staging area: cut the tree instead
+    for (int i = threadIdx.x; fits && i < 2 * nf; i += blockDim.x)
     {
       double2 v = src[i];
       bad |= !(fabs(v.x) < 1e300) || !(fabs(v.y) < 1e300);
-      if (i & 1) v.y += FQ_ROW_TOL;
+      if (i & 1) v.y += a.row_tol;
       dst[i] = v;
     }
     for (int i = threadIdx.x; i <= P && i < 36; i += blockDim.x) sfo[i] = a.face_ofs[p0 + i] - f0;
     rows_bad = __syncthreads_or(bad) != 0;
+    if (!fits) { if (threadIdx.x == 0) b.flags[0] = 1; return; }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long child = (long long)blockIdx.x * W + warp;
@@ -192,8 +194,8 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
   unsigned bcode = 0;
   if (k == 0) update_Y<D, true>(m, TZ, Yeq, bthr, SY, lane, bkey, bcode);
   else update_Y<D, false>(m, TZ, Yeq, bthr, SY, lane, bkey, bcode);
-  const int status = gi_loop<D>(m, TZ, SY, sAb, Yeq, bthr, lane, total_rows, inv1, inv2, inv3, lim0, lim1, lim2, lam, rdinv,
-                                q, it, bkey, bcode);
+  const int status = gi_loop<D>(m, TZ, SY, sAb, Yeq, bthr, lane, total_rows, inv1, inv2, inv3, lim0, lim1, lim2, a.row_tol,
+                                lam, rdinv, q, it, bkey, bcode);
   if (status != 1)
   {
     if (status == -1 && lane == 0) atomicAdd(b.flags + 1, 1);

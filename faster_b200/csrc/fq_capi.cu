@@ -1,7 +1,5 @@
 // C ABI of faster_b200 (see include/faster_b200.h): context, plan cache, host<->device staging, launches.
-#include "../../include/faster_b200.h"
-#include "fq_kernels.cuh"
-#include "fq_plan.h"
+#include "fq_ctx.h"
 
 #include <algorithm>
 #include <chrono>
@@ -12,97 +10,27 @@
 #include <string>
 #include <vector>
 
-namespace
-{
-struct PlanDev
-{
-  FqPlanHost h;
-  double *TZ = nullptr, *T0 = nullptr, *FT = nullptr;
-};
-
-struct Arena
-{ // grow-only device buffer
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t n)
-  {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    size_t want = n + n / 4 + 4096;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct PinnedArena
-{
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t n)
-  {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
-    size_t want = n + n / 4 + 4096;
-    cudaError_t e = cudaMallocHost(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
 std::string g_create_error;
-}  // namespace
 
-struct fq_ctx
-{
-  int device = 0;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t ev_head = nullptr;
-  std::map<int, PlanDev> plans;   // key N*2+force_final
-  Arena d_in, d_out, d_bnb;
-  PinnedArena h_in, h_out;
-  std::string err;
-  bool force_generic = false;
-  int sm_count = 0;
-  int* d_counters = nullptr;      // ring of per-problem claim counters (one slot per launch in flight)
-  int counters_cap = 0;           // problems per slot
-  unsigned counters_pos = 0;
-  bool pending = false;           // a deferred fq_solve_multi_async is still using the arenas (settled by the next call / fq_wait)
-  int throughput_slices = 0;      // option "throughput_slices": launches a large host batch is cut into (0 = default 4)
-  int max_poly_faces_hint = 0;    // option "max_faces_per_polytope" (device-pointer API only)
-};
-static const int kCounterSlots = 64;
-
-namespace
-{
-int fail(fq_ctx* c, int code, const std::string& msg)
+int fq_fail(fq_ctx* c, int code, const std::string& msg)
 {
   if (c) c->err = msg; else g_create_error = msg;
   return code;
 }
-int cuda_fail(fq_ctx* c, cudaError_t e, const char* what)
+int fq_cuda_fail(fq_ctx* c, cudaError_t e, const char* what)
 {
-  return fail(c, FQ_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return fq_fail(c, FQ_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
-#define FQ_CUDA(call)                                          \
-  do {                                                         \
-    cudaError_t e__ = (call);                                  \
-    if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
-  } while (0)
 
-int get_plan(fq_ctx* ctx, int N, int force_final, PlanDev** out)
+int fq_get_plan(fq_ctx* ctx, int N, int force_final, FqPlanDev** out)
 {
   const int key = N * 2 + (force_final ? 1 : 0);
   auto it = ctx->plans.find(key);
   if (it == ctx->plans.end())
   {
-    PlanDev pd;
+    FqPlanDev pd;
     if (!fq_build_plan(N, force_final ? 1 : 0, &pd.h))
-      return fail(ctx, FQ_E_ARG, "unsupported N (need ne <= N <= FQ_MAX_N)");
+      return fq_fail(ctx, FQ_E_ARG, "unsupported N (need ne <= N <= FQ_MAX_N)");
     FQ_CUDA(cudaMalloc(&pd.TZ, sizeof(double) * (pd.h.TZ.size() + 1)));
     FQ_CUDA(cudaMalloc(&pd.T0, sizeof(double) * pd.h.T0.size()));
     FQ_CUDA(cudaMalloc(&pd.FT, sizeof(double) * pd.h.FT.size()));
@@ -115,17 +43,23 @@ int get_plan(fq_ctx* ctx, int N, int force_final, PlanDev** out)
   return 0;
 }
 
-void fill_plan_args(const PlanDev& pd, FqKernelArgs* a)
+void fq_fill_plan_args(const FqPlanDev& pd, FqKernelArgs* a)
 {
   a->N = pd.h.N; a->force_final = pd.h.force_final; a->ne = pd.h.ne; a->nz = pd.h.nz;
   a->nw = 3 * pd.h.nz; a->NY = pd.h.NY; a->ld = (3 * pd.h.nz) | 1;
   a->TZ = pd.TZ; a->T0 = pd.T0; a->FT = pd.FT;
 }
 
-inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-
+namespace
+{
+inline int fail(fq_ctx* c, int code, const std::string& msg) { return fq_fail(c, code, msg); }
+inline size_t align16(size_t x) { return fq_align16(x); }
 inline bool all_finite(const double* p, size_t n) { return fq_scan_all_finite(p, n); }
 inline bool all_positive_finite(const double* p, size_t n) { return fq_scan_all_positive_finite(p, n); }
+typedef FqPlanDev PlanDev;
+inline int get_plan(fq_ctx* ctx, int N, int force_final, PlanDev** out) { return fq_get_plan(ctx, N, force_final, out); }
+inline void fill_plan_args(const PlanDev& pd, FqKernelArgs* a) { fq_fill_plan_args(pd, a); }
+const int kCounterSlots = kFqCounterSlots;
 }  // namespace
 
 extern "C" int fq_create(fq_ctx** out, int device)
@@ -161,9 +95,13 @@ extern "C" int fq_create(fq_ctx** out, int device)
 extern "C" void fq_destroy(fq_ctx* ctx)
 {
   if (!ctx) return;
+  fq_comm_release(ctx);                            // NCCL communicator(s), if any (fq_multi.cu)
+  for (fq_ctx* p : ctx->peers) fq_destroy(p);      // fq_create_multi: the other devices' contexts
+  ctx->peers.clear();
   cudaSetDevice(ctx->device);
   for (auto& kv : ctx->plans) { cudaFree(kv.second.TZ); cudaFree(kv.second.T0); cudaFree(kv.second.FT); }
-  ctx->d_in.release(); ctx->d_out.release(); ctx->d_bnb.release(); ctx->h_in.release(); ctx->h_out.release();
+  ctx->d_in.release(); ctx->d_out.release(); ctx->d_bnb.release(); ctx->d_pair.release(); ctx->d_pair_io.release();
+  ctx->h_in.release(); ctx->h_out.release();
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->ev_head) cudaEventDestroy(ctx->ev_head);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -177,15 +115,19 @@ extern "C" int fq_set_option(fq_ctx* ctx, const char* key, int value)
   if (std::string(key) == "force_generic_kernel") { ctx->force_generic = value != 0; return 0; }
   if (std::string(key) == "throughput_slices") { ctx->throughput_slices = value > 0 && value <= 64 ? value : 0; return 0; }
   if (std::string(key) == "max_faces_per_polytope") { ctx->max_poly_faces_hint = value > 0 ? value : 0; return 0; }
+  if (std::string(key) == "row_tol_1e9")
+  { // row tolerance in units of 1e-9 (10 = the default 1e-8, 1000 = Gurobi's default FeasibilityTol 1e-6); >= 0
+    if (value < 0 || value > 1000000) return fail(ctx, FQ_E_ARG, "row_tol_1e9 out of range (0..1000000)");
+    ctx->row_tol = 1e-9 * (double)value;
+    return 0;
+  }
   return fail(ctx, FQ_E_ARG, std::string("unknown option ") + key);
 }
 
 extern "C" const char* fq_last_error(const fq_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-namespace
-{
 // common launch: every pointer is a device pointer
-int launch_solve(fq_ctx* ctx, int N, int force_final, int n_prob, const double* d_x0, const double* d_xf,
+int fq_launch_solve_ctx(fq_ctx* ctx, int N, int force_final, int n_prob, const double* d_x0, const double* d_xf,
                  const double* d_lim, const int* d_poly_ofs, const int* d_face_ofs, const double* d_Ab,
                  const int* d_cand_ofs, int max_cand, int max_faces, int max_poly_faces, const double* d_dt,
                  const uint8_t* d_sigma, uint8_t* d_feasible, double* d_cost, double* d_coeffs, int32_t* d_iters,
@@ -199,7 +141,7 @@ int launch_solve(fq_ctx* ctx, int N, int force_final, int n_prob, const double* 
   a.n_prob = n_prob; a.x0 = d_x0; a.xf = d_xf; a.lim = d_lim; a.poly_ofs = d_poly_ofs; a.face_ofs = d_face_ofs;
   a.Ab = d_Ab; a.max_faces = max_faces > 0 ? max_faces : 1;
   a.item_cap = N * (max_poly_faces > 0 && max_poly_faces <= a.max_faces ? max_poly_faces : a.max_faces); a.cand_ofs = d_cand_ofs; a.dt = d_dt; a.sigma = d_sigma;
-  a.feasible = d_feasible; a.cost = d_cost; a.coeffs = d_coeffs; a.iters = d_iters;
+  a.feasible = d_feasible; a.cost = d_cost; a.coeffs = d_coeffs; a.iters = d_iters; a.row_tol = ctx->row_tol;
   if (fq_solve_smem_bytes(a) > 227 * 1024)
     return fail(ctx, FQ_E_ARG, "problem too large for shared memory (N / faces per problem)");
   static const bool env_generic = std::getenv("FQ_KERNEL") && std::string(std::getenv("FQ_KERNEL")) == "generic";
@@ -214,6 +156,17 @@ int launch_solve(fq_ctx* ctx, int N, int force_final, int n_prob, const double* 
   int* counters = ctx->d_counters + (size_t)(ctx->counters_pos++ % kCounterSlots) * ctx->counters_cap;
   FQ_CUDA(fq_launch_solve(a, max_cand, stream, counters, ctx->sm_count, env_generic || ctx->force_generic));
   return 0;
+}
+namespace
+{
+inline int launch_solve(fq_ctx* ctx, int N, int force_final, int n_prob, const double* d_x0, const double* d_xf,
+                        const double* d_lim, const int* d_poly_ofs, const int* d_face_ofs, const double* d_Ab,
+                        const int* d_cand_ofs, int max_cand, int max_faces, int max_poly_faces, const double* d_dt,
+                        const uint8_t* d_sigma, uint8_t* d_feasible, double* d_cost, double* d_coeffs, int32_t* d_iters,
+                        cudaStream_t stream)
+{
+  return fq_launch_solve_ctx(ctx, N, force_final, n_prob, d_x0, d_xf, d_lim, d_poly_ofs, d_face_ofs, d_Ab, d_cand_ofs, max_cand,
+                             max_faces, max_poly_faces, d_dt, d_sigma, d_feasible, d_cost, d_coeffs, d_iters, stream);
 }
 }  // namespace
 
@@ -234,11 +187,10 @@ extern "C" int fq_solve_multi_dev(fq_ctx* ctx, int N, int force_final, int n_pro
                       d_coeffs, d_iters, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
-namespace
+int fq_settle(fq_ctx* ctx)
 {
-// a deferred call owns the context's arenas until it has drained: every entry point that reuses them settles first
-int settle(fq_ctx* ctx)
-{
+  for (fq_ctx* p : ctx->peers)                     // a multi-GPU group settles every member
+    if (int rc = fq_settle(p)) { ctx->err = p->err; return rc; }
   if (!ctx->pending) return 0;
   ctx->pending = false;
   FQ_CUDA(cudaSetDevice(ctx->device));
@@ -246,6 +198,9 @@ int settle(fq_ctx* ctx)
   FQ_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+namespace
+{
+inline int settle(fq_ctx* ctx) { return fq_settle(ctx); }
 }  // namespace
 
 namespace
@@ -253,7 +208,7 @@ namespace
 struct HostLayout
 { // byte offsets of each array inside the input / output arenas
   size_t x0, xf, lim, dt, Ab, poly_ofs, face_ofs, cand_ofs, sigma, in_bytes;
-  size_t cost, coeffs, iters, feasible, out_bytes;
+  size_t cost, coeffs, iters, feasible, win_cost, win_dt, win_idx, win_ofs, out_bytes;
 };
 
 // validates the host description and computes sizes
@@ -300,8 +255,12 @@ int describe(fq_ctx* ctx, int N, int force_final, int n_prob, const int* poly_of
   L->in_bytes = align16(o);
   o = 0;
   L->cost = o;      o += sizeof(double) * (size_t)*n_cand;
+  L->win_cost = o;  o += sizeof(double) * (size_t)n_prob;       // per-problem winners (fq_solve_multi_sharded)
+  L->win_dt = o;    o += sizeof(double) * (size_t)n_prob;
   L->coeffs = o;    o += want_coeffs ? sizeof(double) * 12 * (size_t)N * (size_t)*n_cand : 0;
   L->iters = o;     o += want_iters ? sizeof(int32_t) * (size_t)*n_cand : 0;
+  L->win_idx = o;   o += sizeof(int) * (size_t)n_prob;
+  L->win_ofs = o;   o += sizeof(int) * (size_t)(n_prob + 1);
   L->feasible = o;  o += (size_t)*n_cand;
   L->out_bytes = align16(o);
   return 0;
@@ -333,7 +292,7 @@ namespace
 int solve_multi_impl(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf,
                      const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
                      const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible,
-                     double* cost, double* coeffs, int32_t* iters, bool deferred)
+                     double* cost, double* coeffs, int32_t* iters, bool deferred, HostLayout* L_out = nullptr)
 {
   if (!ctx) return FQ_E_ARG;
   if (int src = settle(ctx)) return src;
@@ -345,6 +304,7 @@ int solve_multi_impl(fq_ctx* ctx, int N, int force_final, int n_prob, const doub
   int rc = describe(ctx, N, force_final, n_prob, poly_ofs, face_ofs, cand_ofs, sigma, coeffs != nullptr,
                     iters != nullptr, &L, &n_cand, &n_poly, &n_face, &max_cand, &max_faces, &max_poly_faces);
   if (rc) return rc;
+  if (L_out) *L_out = L;
   tr.mark("describe");
   if (n_cand == 0) return 0;
   if (n_poly > 0 && (!Ab || !sigma)) return fail(ctx, FQ_E_ARG, "polytopes given but Ab or sigma is NULL");
@@ -500,10 +460,42 @@ extern "C" int fq_solve_multi_async(fq_ctx* ctx, int N, int force_final, int n_p
                           coeffs, iters, true);
 }
 
+// fq_solve_multi_async + the genNewTraj winner of every problem, selected on the device (the arrays stay in the context's
+// output arena until the next call): what the multi-GPU path all-gathers (fq_multi.cu)
+int fq_solve_multi_host_ex(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf, const double* lim,
+                           const int* poly_ofs, const int* face_ofs, const double* Ab, const int* cand_ofs, const double* dt,
+                           const uint8_t* sigma, uint8_t* feasible, double* cost, double* coeffs, int32_t* iters, bool deferred,
+                           int** d_win_idx, double** d_win_cost)
+{
+  HostLayout L;
+  int rc = solve_multi_impl(ctx, N, force_final, n_prob, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dt, sigma, feasible, cost,
+                            coeffs, iters, true, &L);
+  if (rc) return rc;
+  if (cand_ofs[n_prob] == 0) return fail(ctx, FQ_E_ARG, "no candidates");
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  // slices of a large batch alternate between the two streams: join before selecting
+  FQ_CUDA(cudaEventRecord(ctx->ev_head, ctx->stream2));
+  FQ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_head, 0));
+  char* din = (char*)ctx->d_in.p;
+  char* dout = (char*)ctx->d_out.p;
+  FqSelectMultiArgs sa;
+  sa.n_prob = n_prob; sa.N = N; sa.n_sig = 0; sa.cand_ofs = (const int*)(din + L.cand_ofs); sa.dt = (const double*)(din + L.dt);
+  sa.sigma = nullptr; sa.feasible = (const uint8_t*)(dout + L.feasible); sa.cost = (const double*)(dout + L.cost);
+  sa.win_idx = (int*)(dout + L.win_idx); sa.win_cost = (double*)(dout + L.win_cost); sa.win_dt = (double*)(dout + L.win_dt);
+  sa.win_sigma = nullptr; sa.win_ofs = (int*)(dout + L.win_ofs);
+  FQ_CUDA(fq_launch_select_multi(sa, ctx->stream));
+  if (d_win_idx) *d_win_idx = sa.win_idx;
+  if (d_win_cost) *d_win_cost = sa.win_cost;
+  ctx->pending = true;
+  if (!deferred) return settle(ctx);
+  return 0;
+}
+
 extern "C" int fq_wait(fq_ctx* ctx)
 {
   if (!ctx) return FQ_E_ARG;
   ctx->pending = true;          // also drains device-pointer launches made on the context's own stream
+  for (fq_ctx* p : ctx->peers) p->pending = true;
   return settle(ctx);
 }
 
@@ -684,6 +676,7 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
   if (int src = settle(ctx)) return src;
   if (!x0 || !xf || !lim || !dts || n_dt <= 0) return fail(ctx, FQ_E_ARG, "NULL argument or n_dt <= 0");
   if (P < 0 || P > FQ_MAX_POLY) return fail(ctx, FQ_E_ARG, "bad P");
+  if (N < (force_final ? 3 : 2) || N > FQ_MAX_N) return fail(ctx, FQ_E_ARG, "N out of range");
   if (nodes_out) *nodes_out = 0;
   if (exact_out) *exact_out = 1;
   if (sigma_out) std::memset(sigma_out, 0, (size_t)N);
@@ -698,8 +691,11 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
   // ---- 1. non-decreasing assignments for every time allocation: the ordinary sweep (one launch + selection).  Its winner
   //         is the first monotone-feasible time allocation `fstar` with that allocation's best monotone cost; earlier
   //         allocations have no feasible monotone assignment, later ones cannot win.
-  const long n_mono = fq_monotone_sigmas(N, P, nullptr, 0);
-  if (n_mono <= 0 || n_mono > (1L << 20)) return fail(ctx, FQ_E_ARG, "assignment list too long");
+  // C(N+P-1, N) in closed form (enumerating to count would take hours for large N and P)
+  long n_mono = 1;
+  for (int i = 1; i <= N && n_mono <= (1L << 40); i++) n_mono = n_mono * (P - 1 + i) / i;
+  if (n_mono <= 0 || n_mono > (1L << 20) || (long long)n_mono * n_dt > (1LL << 24))
+    return fail(ctx, FQ_E_ARG, "assignment list too long for the monotone pre-sweep (N, P, n_dt too large)");
   std::vector<uint8_t> mono((size_t)n_mono * N);
   fq_monotone_sigmas(N, P, mono.data(), n_mono);
   int m_dt = -1, m_sig = -1;
@@ -754,7 +750,7 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
       {
         bool in = true;
         for (int f = face_ofs[p]; f < face_ofs[p + 1] && in; f++)
-          in = Ab[4 * f] * pt[0] + Ab[4 * f + 1] * pt[1] + Ab[4 * f + 2] * pt[2] - Ab[4 * f + 3] <= FQ_ROW_TOL;
+          in = Ab[4 * f] * pt[0] + Ab[4 * f + 1] * pt[1] + Ab[4 * f + 2] * pt[2] - Ab[4 * f + 3] <= ctx->row_tol;
         if (in) return true;
       }
       return false;
@@ -782,7 +778,7 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
             for (int ax = 0; ax < 3; ax++)
               pt[ax] = x0[ax] + (kk >= 1 ? x0[3 + ax] * t * (kk == 1 ? 1.0 / 3.0 : 2.0 / 3.0) : 0.0) + (kk == 2 ? x0[6 + ax] * t * t / 6.0 : 0.0);
             for (int f = face_ofs[p]; f < face_ofs[p + 1] && in; f++)
-              in = Ab[4 * f] * pt[0] + Ab[4 * f + 1] * pt[1] + Ab[4 * f + 2] * pt[2] - Ab[4 * f + 3] <= FQ_ROW_TOL;
+              in = Ab[4 * f] * pt[0] + Ab[4 * f + 1] * pt[1] + Ab[4 * f + 2] * pt[2] - Ab[4 * f + 3] <= ctx->row_tol;
           }
           possible = in;
         }
@@ -801,7 +797,7 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
     L.k.n_prob = 1; L.k.x0 = (const double*)(db + ox0); L.k.xf = (const double*)(db + oxf); L.k.lim = (const double*)(db + olim);
     L.k.poly_ofs = (const int*)(db + opo); L.k.face_ofs = (const int*)(db + ofo); L.k.Ab = (const double*)(db + oAb);
     L.k.max_faces = n_face; L.k.item_cap = N * max_pf; L.k.cand_ofs = nullptr; L.k.dt = nullptr; L.k.sigma = nullptr;
-    L.k.feasible = nullptr; L.k.cost = nullptr; L.k.coeffs = nullptr; L.k.iters = nullptr;
+    L.k.feasible = nullptr; L.k.cost = nullptr; L.k.coeffs = nullptr; L.k.iters = nullptr; L.k.row_tol = ctx->row_tol;
     L.n_dt = n_dt; L.P = P; L.dts = (const double*)(db + odts); L.roots = (const int*)(db + oroot);
     L.incumbent = (unsigned long long*)(db + oinc); L.leaves = db + oleaf; L.n_leaves = (int*)(db + ocnt) + 1;
     L.leaf_cap = leaf_cap; L.flags = (int*)(db + ocnt) + 2; L.n_children = (int*)(db + ocnt); L.cap = cap;
@@ -821,6 +817,8 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
       FQ_CUDA(cudaStreamSynchronize(st));
       nodes += (long)n_par * P;
       if (cnt[2]) { exact = false; break; }                      // pool overflow: the tree was cut
+      if (cnt[3]) { exact = false; break; }                      // a node hit the iteration cap / a NaN and its subtree was
+                                                                 // dropped: the optimum may hide there, so not exact
       n_par = cnt[0];
     }
     if (nodes_out) *nodes_out = nodes;

@@ -1,5 +1,6 @@
 // Host-side pieces of the hot path that need no GPU: plan tables, getDTInitial, resetX/fillX, sigma lists.
 #include "fq_plan.h"
+#include "fq_dtinit.h"
 #include "../../include/faster_b200.h"
 
 #include <algorithm>
@@ -147,87 +148,12 @@ bool fq_build_plan(int N, int force_final, FqPlanHost* plan)
 // arithmetic; the same conversions are made here.  Its roots come from Eigen's companion-matrix solver; here
 // from closed forms refined by Newton steps, then rounded to float exactly as the reference's assignments do.
 // ---------------------------------------------------------------------------------------------------------
-namespace
-{
-int roots2(double c0, double c1, double c2, double* r)
-{
-  double disc = c1 * c1 - 4 * c2 * c0;
-  if (disc < 0) return 0;
-  double sq = std::sqrt(disc);
-  double q = -0.5 * (c1 + (c1 >= 0 ? sq : -sq));
-  r[0] = q / c2;
-  r[1] = q != 0 ? c0 / q : 0.0;
-  return 2;
-}
-
-int roots3(double c0, double c1, double c2, double c3, double* r)
-{
-  const double a = c2 / c3, b = c1 / c3, c = c0 / c3;
-  const double Q = (a * a - 3 * b) / 9, R = (2 * a * a * a - 9 * a * b + 27 * c) / 54;
-  int k = 0;
-  if (R * R < Q * Q * Q)
-  {
-    const double th = std::acos(R / std::sqrt(Q * Q * Q)), m = -2 * std::sqrt(Q);
-    const double two_pi = 6.283185307179586476925286766559;
-    r[k++] = m * std::cos(th / 3) - a / 3;
-    r[k++] = m * std::cos((th + two_pi) / 3) - a / 3;
-    r[k++] = m * std::cos((th - two_pi) / 3) - a / 3;
-  }
-  else
-  {
-    const double A = -std::copysign(std::cbrt(std::fabs(R) + std::sqrt(R * R - Q * Q * Q)), R);
-    const double B = A != 0 ? Q / A : 0;
-    r[k++] = A + B - a / 3;
-    if (R * R == Q * Q * Q && Q != 0) r[k++] = -0.5 * (A + B) - a / 3;
-  }
-  for (int i = 0; i < k; i++)
-    for (int it = 0; it < 3; it++)
-    {
-      const double t = r[i], f = ((c3 * t + c2) * t + c1) * t + c0, fp = (3 * c3 * t + 2 * c2) * t + c1;
-      if (fp != 0 && std::isfinite(f / fp)) r[i] = t - f / fp;
-    }
-  return k;
-}
-
-// MinPositiveElement (solverGurobi_utils.hpp:19-32)
-double min_positive(const double* v, int n)
-{
-  double best = 0;
-  bool found = false;
-  for (int i = 0; i < n; i++)
-    if (v[i] > 0 && (!found || v[i] < best)) { best = v[i]; found = true; }
-  return best;
-}
-}  // namespace
-
 extern "C" double fq_dt_initial(const double* x0, const double* xf, const double* lim, int N)
 {
-  const double v_max = lim[0], a_max = lim[1], j_max = lim[2];
-  float worst = 0;
-  for (int i = 0; i < 3; i++)
-  {
-    const double dp = xf[i] - x0[i];
-    const float t_v = (float)(std::fabs(dp) / v_max);                 // :672-674
-    const float jerk = (float)(std::copysign(1.0, dp) * j_max);       // :679-681
-    const float accel = (float)(std::copysign(1.0, dp) * a_max);      // :718-720
-    const float a0 = (float)x0[6 + i], v0 = (float)x0[3 + i];         // :682-687
-    double r[3];
-    int k = roots3(x0[i] - xf[i], v0, a0 / 2.0, jerk / 6.0, r);       // :691-713
-    const float t_j = (float)min_positive(r, k);
-    k = roots2(x0[i] - xf[i], v0, 0.5 * accel, r);                    // :724-746
-    const float t_a = (float)min_positive(r, k);
-    worst = std::max(worst, std::max(t_v, std::max(t_a, t_j)));
-  }
-  double dt_initial = (double)(worst / (float)N);                     // float / int (:751)
-  if (dt_initial > 10000) dt_initial = 0;                             // :752-756
-  return dt_initial;
+  return fqdt::dt_initial(x0, xf, lim, N);       // fq_dtinit.h: one source for host and device
 }
 
-extern "C" int fq_num_samples(int N, double dt, double DC)
-{ // resetX (:382-388): (int)(N_)*dt_/DC truncated to int, at least 2
-  int size = (int)((int)(N)*dt / DC);
-  return size < 2 ? 2 : size;
-}
+extern "C" int fq_num_samples(int N, double dt, double DC) { return fqdt::num_samples(N, dt, DC); }
 
 extern "C" void fq_fill_x(int N, const double* coeffs, double dt, double DC, int n_samples, double* out)
 { // fillX (:122-168): time accumulates by DC; the interval index advances by at most one per sample
@@ -238,15 +164,7 @@ extern "C" void fq_fill_x(int N, const double* coeffs, double dt, double DC, int
     t = t + DC;
     if (t > dt * (interval + 1)) interval = std::min(interval + 1, N - 1);
     const double tau = t - interval * dt;
-    const double* x = coeffs + 12 * interval;
-    double* o = out + (size_t)12 * i;
-    for (int ax = 0; ax < 3; ax++)
-    {
-      o[ax] = x[ax] * tau * tau * tau + x[3 + ax] * tau * tau + x[6 + ax] * tau + x[9 + ax];
-      o[3 + ax] = 3 * x[ax] * tau * tau + 2 * x[3 + ax] * tau + x[6 + ax];
-      o[6 + ax] = 6 * x[ax] * tau + 2 * x[3 + ax];
-      o[9 + ax] = 6 * x[ax];
-    }
+    fqdt::eval_sample(coeffs + 12 * interval, tau, out + (size_t)12 * i);
   }
   if (n_samples > 0)
     for (int k = 3; k < 12; k++) out[(size_t)12 * (n_samples - 1) + k] = 0.0;   // :165-167

@@ -108,7 +108,7 @@ __device__ __forceinline__ void drop_row(const FqKernelArgs& a, const WarpMem& m
 }
 
 __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const double* T0, const double* sAb,
-                                const int* sfo, const WarpMem& m, int prob, int cand, int lane, bool rows_bad)
+                                const int* sfo, const WarpMem& m, int prob, int cand, int lane, int rows_bad)
 {
   const int N = a.N, nz = a.nz, nw = a.nw, NY = a.NY, ld = a.ld, ne = a.ne;
   const double dt = a.dt[cand], dt2 = dt * dt;
@@ -166,7 +166,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
   int q = 0, status = -1, it = 0;
   { // non-finite / non-positive inputs (unvalidated device-pointer entry): report "not solved", never fault
     bool okc = dt > 0 && dt < 1e100 && lim0 > 0 && lim0 < 1e300 && lim1 > 0 && lim1 < 1e300 && lim2 > 0 && lim2 < 1e300 &&
-               !rows_bad;
+               rows_bad == 0;
     for (int idx = lane; idx < 3 * NY; idx += 32) okc = okc && fabs(m.Yeq[idx]) < 1e300;
     if (!__all_sync(FULL, okc))
     {
@@ -174,7 +174,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
       {
         a.feasible[cand] = 0;
         a.cost[cand] = INFINITY;
-        if (a.iters) a.iters[cand] = -1;
+        if (a.iters) a.iters[cand] = rows_bad == 2 ? -2 : -1;
       }
       if (a.coeffs)
         for (int idx = lane; idx < 12 * N; idx += 32) a.coeffs[(size_t)cand * N * 12 + idx] = 0.0;
@@ -184,7 +184,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
   for (;;)
   {
     // ================= most violated row =================
-    double bv = FQ_ROW_TOL, bw0 = 0, bw1 = 0, bw2 = 0, bh = 0;
+    double bv = a.row_tol, bw0 = 0, bw1 = 0, bw2 = 0, bh = 0;
     int by = 0;
     for (int i = lane; i < 9 * N; i += 32)
     { // |v|,|a|,|j| boxes at segment starts (solverGurobi.cpp:390-407); type 0 v, 1 a, 2 j
@@ -217,7 +217,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
         if (v > bv) { bv = v; by = y; bw0 = a01.x; bw1 = a01.y; bw2 = a23.x; bh = a23.y; }
       }
     }
-    const unsigned key = bv > FQ_ROW_TOL ? __float_as_uint(fmaxf((float)bv, 1e-30f)) : 0u;
+    const unsigned key = bv > a.row_tol ? __float_as_uint(fmaxf((float)bv, 1e-30f)) : 0u;
     const unsigned mk = __reduce_max_sync(FULL, key);
     if (mk == 0u) { status = 1; break; }
     const int src = __ffs(__ballot_sync(FULL, key == mk)) - 1;
@@ -385,19 +385,21 @@ __global__ void __launch_bounds__(W * 32) fq_solve_kernel(const FqKernelArgs a, 
   const int p0 = a.poly_ofs[prob], P = a.poly_ofs[prob + 1] - p0;
   const int f0 = a.face_ofs[p0];
   const int nf = P > 0 ? a.face_ofs[p0 + P] - f0 : 0;
-  bool rows_bad = false;
+  int rows_bad = 0;
   {
+    const bool fits = nf >= 0 && nf <= a.max_faces;   // a too small max_faces hint must not overrun the staging area
     const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
     double2* dst = reinterpret_cast<double2*>(sAb);
     int bad = 0;
-    for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x)
+    for (int i = threadIdx.x; fits && i < 2 * nf; i += blockDim.x)
     {
       const double2 v = src[i];
       bad |= !(fabs(v.x) < 1e300) || !(fabs(v.y) < 1e300);
       dst[i] = v;
     }
     for (int i = threadIdx.x; i <= P && i < 36; i += blockDim.x) sfo[i] = a.face_ofs[p0 + i] - f0;
-    rows_bad = __syncthreads_or(bad) != 0;
+    rows_bad = __syncthreads_or(bad) != 0 ? 1 : 0;
+    if (!fits) rows_bad = 2;
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -512,6 +514,7 @@ __global__ void __launch_bounds__(256) fq_fill_kernel(const FqFillArgs a)
 
 #include "fq_kernels_t.cuh"
 #include "fq_bnb.cuh"
+#include "fq_pair.cuh"
 
 size_t fq_solve_smem_bytes(const FqKernelArgs& a)
 {
@@ -604,4 +607,46 @@ cudaError_t fq_launch_bnb_level(const FqBnbLevel& l, cudaStream_t stream)
     default: return cudaErrorInvalidConfiguration;
   }
 #undef FQ_CASE
+}
+
+cudaError_t fq_launch_dtbase(int n_prob, int N, double DC, const double* x0, const double* xf, const double* lim,
+                             double* dt_base, cudaStream_t stream)
+{
+  if (n_prob <= 0) return cudaSuccess;
+  fqp::fq_dtbase_kernel<<<(n_prob + 127) / 128, 128, 0, stream>>>(n_prob, N, DC, x0, xf, lim, dt_base);
+  return cudaGetLastError();
+}
+
+cudaError_t fq_launch_expand_grid(int n_prob, int N, int n_fac, int n_sig, const double* factors, const uint8_t* sig_list,
+                                  const double* dt_base, double* dt, uint8_t* sigma, int* cand_ofs, cudaStream_t stream)
+{
+  if (n_prob <= 0) return cudaSuccess;
+  const long long total = (long long)n_prob * n_fac * n_sig;
+  long long blocks = (total + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fqp::fq_expand_grid_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n_prob, N, n_fac, n_sig, factors, sig_list, dt_base, dt, sigma,
+                                                                  cand_ofs);
+  return cudaGetLastError();
+}
+
+cudaError_t fq_launch_select_multi(const FqSelectMultiArgs& a, cudaStream_t stream)
+{
+  if (a.n_prob <= 0) return cudaSuccess;
+  fqp::fq_select_multi_kernel<<<a.n_prob, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t fq_launch_pair_mid(const FqPairMidArgs& a, cudaStream_t stream)
+{
+  if (a.n_prob <= 0) return cudaSuccess;
+  fqp::fq_pair_mid_kernel<<<(a.n_prob + 63) / 64, 64, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t fq_launch_pair_final(const FqPairFinalArgs& a, cudaStream_t stream)
+{
+  if (a.n_prob <= 0) return cudaSuccess;
+  fqp::fq_pair_final_kernel<<<(a.n_prob + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
 }

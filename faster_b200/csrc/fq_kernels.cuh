@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "../../include/faster_b200.h"
 
 #define FQ_WARPS_PER_CTA 4
 #ifndef FQ_MIN_CTAS_PER_SM
@@ -52,6 +53,7 @@ struct FqKernelArgs
   double* cost;
   double* coeffs;        // n_cand x N x 12 or nullptr
   int32_t* iters;        // or nullptr
+  double row_tol;        // absolute row tolerance (default FQ_ROW_TOL; option "row_tol_1e9")
 };
 
 struct FqSelectArgs
@@ -108,3 +110,47 @@ struct FqBnbLevel
 };
 size_t fq_bnb_node_bytes(int N, int force_final);     // 0 if unsupported
 cudaError_t fq_launch_bnb_level(const FqBnbLevel& l, cudaStream_t stream);
+
+// ---- chained replan (fq_pair.cuh): the small kernels between the whole and the safe sweep
+struct FqSelectMultiArgs
+{
+  int n_prob, N, n_sig;                 // n_sig > 0: candidates are a (factor x assignment) grid, dt index = local / n_sig
+  const int* cand_ofs;
+  const double* dt;
+  const uint8_t* sigma;
+  const uint8_t* feasible;
+  const double* cost;
+  int* win_idx;                         // n_prob: candidate index relative to the problem's first candidate, -1 none
+  double* win_cost;                     // n_prob (+inf none)
+  double* win_dt;                       // n_prob (NaN none): also the dt list of the winners' re-solve
+  uint8_t* win_sigma;                   // n_prob x N
+  int* win_ofs;                         // n_prob + 1: 0,1,2,... (cand_ofs of the re-solve)
+};
+
+struct FqPairMidArgs
+{
+  int n_prob, N;
+  double DC, r_fraction;
+  const double* coeffs;                 // n_prob x N x 12: the whole winners
+  const double* win_dt;                 // n_prob (NaN: no winner)
+  const int* win_idx;
+  double* x0_safe;                      // n_prob x 9 (NaN when there is no whole trajectory to branch from)
+  int* n_samples;                       // n_prob
+  int* k_safe;                          // n_prob
+};
+
+struct FqPairFinalArgs
+{
+  int n_prob, n_sig_w, n_sig_s;
+  const int *win_idx_w, *win_idx_s, *n_samples, *k_safe;
+  const double *win_cost_w, *win_cost_s, *win_dt_w, *win_dt_s, *dt_base_w, *dt_base_s, *x0_safe;
+  fq_pair_result* out;
+};
+
+cudaError_t fq_launch_dtbase(int n_prob, int N, double DC, const double* x0, const double* xf, const double* lim,
+                             double* dt_base, cudaStream_t stream);
+cudaError_t fq_launch_expand_grid(int n_prob, int N, int n_fac, int n_sig, const double* factors, const uint8_t* sig_list,
+                                  const double* dt_base, double* dt, uint8_t* sigma, int* cand_ofs, cudaStream_t stream);
+cudaError_t fq_launch_select_multi(const FqSelectMultiArgs& a, cudaStream_t stream);
+cudaError_t fq_launch_pair_mid(const FqPairMidArgs& a, cudaStream_t stream);
+cudaError_t fq_launch_pair_final(const FqPairFinalArgs& a, cudaStream_t stream);

@@ -286,9 +286,9 @@ __device__ __forceinline__ void setup_rows(const FqKernelArgs& a, int prob, doub
     {
       const int y = lane + 32 * r;
       // box type of the row: v (rows N+1..2N), a (2N+1..3N), j (3N+1..4N), none otherwise
-      bthr[r] = (y >= N + 1 && y <= 2 * N) ? (lim0 + FQ_ROW_TOL) * dt
-                : ((y >= 2 * N + 1 && y <= 3 * N) ? (lim1 + FQ_ROW_TOL) * dt2
-                                                  : ((y >= 3 * N + 1 && y <= 4 * N) ? (lim2 + FQ_ROW_TOL) * dt2 * dt : 1e300));
+      bthr[r] = (y >= N + 1 && y <= 2 * N) ? (lim0 + a.row_tol) * dt
+                : ((y >= 2 * N + 1 && y <= 3 * N) ? (lim1 + a.row_tol) * dt2
+                                                  : ((y >= 3 * N + 1 && y <= 4 * N) ? (lim2 + a.row_tol) * dt2 * dt : 1e300));
 #pragma unroll
       for (int ax = 0; ax < 3; ax++) Yeq[r][ax] = 0.0;
       if (y < NY)
@@ -351,8 +351,9 @@ template <class D>
 __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __restrict__ TZ, const double* __restrict__ SY,
                                        const double* __restrict__ sAb, const double (&Yeq)[D::RPL][3],
                                        const double (&bthr)[D::RPL], int lane, int total_rows, double inv1, double inv2,
-                                       double inv3, double lim0, double lim1, double lim2, double (&lam)[D::SLOTS],
-                                       double (&rdinv)[D::SLOTS], int& q, int& it, int bkey, unsigned bcode)
+                                       double inv3, double lim0, double lim1, double lim2, double row_tol,
+                                       double (&lam)[D::SLOTS], double (&rdinv)[D::SLOTS], int& q, int& it, int bkey,
+                                       unsigned bcode)
 {
   constexpr int N = D::N, NZ = D::NZ, NW = D::NW, NYP = D::NYP, LD = D::LD, SLOTS = D::SLOTS;
   double r[SLOTS], z[SLOTS], dreg[SLOTS];
@@ -402,7 +403,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
       const int t = item >> 12, gf = item & 0x7ff;
       w0 = sAb[4 * gf]; w1 = sAb[4 * gf + 1]; w2 = sAb[4 * gf + 2];
       const double hb = sAb[4 * gf + 3];            // b + tol
-      h = hb - FQ_ROW_TOL;
+      h = hb - row_tol;
       const int ys[4] = { 4 * N + 1 + t, 5 * N + 1 + t, t + 1, t };
       y = ys[0];
       int best = -0x7fffffff;
@@ -639,7 +640,7 @@ template <class D>
 __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict__ TZ,
                                 const double* __restrict__ SY, const double* __restrict__ sAb,
                                 const int* __restrict__ sfo, const WarpState<D>& m, int* __restrict__ seg_ofs,
-                                int prob, int cand, int lane, bool rows_bad)
+                                int prob, int cand, int lane, int rows_bad)
 {
   constexpr int N = D::N, NW = D::NW, NYP = D::NYP, SLOTS = D::SLOTS;
   const double dt = a.dt[cand];
@@ -654,7 +655,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
   //      candidate is reported "not solved" right away.  NaN keys would otherwise rank as "satisfied".
   {
     bool okc = dt > 0 && dt < 1e100 && lim0 > 0 && lim0 < 1e300 && lim1 > 0 && lim1 < 1e300 && lim2 > 0 && lim2 < 1e300 &&
-               !rows_bad;
+               rows_bad == 0;
 #pragma unroll
     for (int r = 0; r < D::RPL; r++)
 #pragma unroll
@@ -665,7 +666,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
       {
         a.feasible[cand] = 0;
         a.cost[cand] = INFINITY;
-        if (a.iters) a.iters[cand] = -1;
+        if (a.iters) a.iters[cand] = rows_bad == 2 ? -2 : -1;   // -2: the problem's rows exceed the max_faces hint
       }
       if (a.coeffs)
         for (int idx = lane; idx < 12 * N; idx += 32) a.coeffs[(size_t)cand * N * 12 + idx] = 0.0;
@@ -712,8 +713,8 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
   int bkey = 0;
   unsigned bcode = 0;
   update_Y<D, true>(m, TZ, Yeq, bthr, SY, lane, bkey, bcode);
-  const int status = gi_loop<D>(m, TZ, SY, sAb, Yeq, bthr, lane, total_rows, inv1, inv2, inv3, lim0, lim1, lim2, lam, rdinv,
-                                q, it, bkey, bcode);
+  const int status = gi_loop<D>(m, TZ, SY, sAb, Yeq, bthr, lane, total_rows, inv1, inv2, inv3, lim0, lim1, lim2, a.row_tol,
+                                lam, rdinv, q, it, bkey, bcode);
 
   // ================= outputs =================
   double cp = 0;
@@ -830,7 +831,9 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
     const int p0 = a.poly_ofs[prob], P = a.poly_ofs[prob + 1] - p0;
     const int f0 = a.face_ofs[p0];
     const int nf = P > 0 ? a.face_ofs[p0 + P] - f0 : 0;
-    bool rows_bad = false;
+    int rows_bad = 0;
+    if (nf > a.max_faces || nf < 0) rows_bad = 2;  // a too small max_faces_per_prob hint (device-pointer entry): never
+    else                                           // overrun the staging area, report the problem "not solved"
     {
       const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
       double2* dst = reinterpret_cast<double2*>(sAb);
@@ -839,11 +842,11 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
       {
         double2 v = src[i];
         bad |= !(fabs(v.x) < 1e300) || !(fabs(v.y) < 1e300);
-        if (i & 1) v.y += FQ_ROW_TOL;              // rows are staged as [Ax Ay Az b+tol]
+        if (i & 1) v.y += a.row_tol;               // rows are staged as [Ax Ay Az b+tol]
         dst[i] = v;
       }
       for (int i = lane; i <= P && i < 36; i += 32) sfo[i] = a.face_ofs[p0 + i] - f0;
-      rows_bad = __any_sync(FULL, bad) != 0;
+      rows_bad = __any_sync(FULL, bad) != 0 ? 1 : 0;
       __syncwarp();                                // publishes the staged rows to the warp
     }
     int c = 0;
@@ -890,20 +893,22 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
     const int p0 = a.poly_ofs[prob], P = a.poly_ofs[prob + 1] - p0;
     const int f0 = a.face_ofs[p0];
     const int nf = P > 0 ? a.face_ofs[p0 + P] - f0 : 0;
-    bool rows_bad = false;
+    int rows_bad = 0;
     {
+      const bool fits = nf >= 0 && nf <= a.max_faces;      // see the warp-adopting variant above
       const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
       double2* dst = reinterpret_cast<double2*>(sAb);
       int bad = 0;
-      for (int i = threadIdx.x; i < 2 * nf; i += blockDim.x)
+      for (int i = threadIdx.x; fits && i < 2 * nf; i += blockDim.x)
       {
         double2 v = src[i];
         bad |= !(fabs(v.x) < 1e300) || !(fabs(v.y) < 1e300);
-        if (i & 1) v.y += FQ_ROW_TOL;              // rows are staged as [Ax Ay Az b+tol]
+        if (i & 1) v.y += a.row_tol;               // rows are staged as [Ax Ay Az b+tol]
         dst[i] = v;
       }
       for (int i = threadIdx.x; i <= P && i < 36; i += blockDim.x) sfo[i] = a.face_ofs[p0 + i] - f0;
-      rows_bad = __syncthreads_or(bad) != 0;       // also the barrier that publishes the staged rows
+      rows_bad = __syncthreads_or(bad) != 0 ? 1 : 0;       // also the barrier that publishes the staged rows
+      if (!fits) rows_bad = 2;
     }
     // claim candidates one ahead: the global atomic for the NEXT candidate is issued before the current one is solved,
     // so its round trip (~1 us) hides behind the solve instead of idling the warp between candidates

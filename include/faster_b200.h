@@ -26,10 +26,11 @@
 extern "C" {
 #endif
 
-#define FQ_ABI_VERSION 1
+#define FQ_ABI_VERSION 2
 #define FQ_MAX_N 16               /* segments per trajectory                                  */
 #define FQ_MAX_POLY 32            /* polytopes per corridor problem                           */
-#define FQ_ROW_TOL 1e-8           /* absolute row violation tolerance (m, m/s, m/s^2, m/s^3)  */
+#define FQ_ROW_TOL 1e-8           /* DEFAULT absolute row violation tolerance (m, m/s, m/s^2, m/s^3); run-time
+                                     option "row_tol_1e9" of fq_set_option                                   */
 
 #define FQ_E_ARG (-1)
 #define FQ_E_CUDA (-2)
@@ -53,7 +54,9 @@ const char* fq_last_error(const fq_ctx* ctx);   /* ctx may be NULL: last creatio
 /* Tuning / testing knobs.  "force_generic_kernel" (0/1): use the size-generic kernel even where a size-specialised one
  * exists (the two are independent implementations of the same solve; tests run both).  "throughput_slices" (1..64, 0 =
  * default: 4, or 2 for fq_solve_multi_async): how many launches a large host batch is cut into (upload / solve / download of consecutive slices
- * overlap on two streams).  "max_faces_per_polytope": see fq_solve_multi_dev.  Returns 0 or FQ_E_ARG. */
+ * overlap on two streams).  "max_faces_per_polytope": see fq_solve_multi_dev.  "row_tol_1e9" (0..1000000): the absolute row
+ * tolerance of every later solve of the context in units of 1e-9 -- 10 is the default FQ_ROW_TOL = 1e-8, 1000 is Gurobi's
+ * default FeasibilityTol 1e-6 (the reference sets no tolerance parameter, solverGurobi.cpp:479-487).  Returns 0 or FQ_E_ARG. */
 int fq_set_option(fq_ctx* ctx, const char* key, int value);
 
 /* One corridor problem, n_cand candidates (dt[i], sigma[i*N .. i*N+N-1]); HOST pointers.
@@ -132,6 +135,110 @@ int fq_gen_new_traj_sampled(fq_ctx* ctx, int N, int force_final, const double* x
 int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf, const double* lim,
                           int P, const int* face_ofs, const double* Ab, int n_dt, const double* dts, int* dt_index,
                           uint8_t* sigma_out, double* cost, double* coeffs, long* nodes_out, int* exact_out);
+
+/* ---- chained replan: whole sweep -> R -> safe sweep, many corridors in one submission ----------------------------
+ *
+ * One Faster::replan() asks its two solver objects (sg_whole_, sg_safe_; faster.hpp:74-75) for two DEPENDENT sweeps:
+ *   sg_whole_.setX0(A); setXf(E); setPolytopes(whole corridor); genNewTraj(); fillX()          faster.cpp:406-430
+ *   R = sg_whole_.X_temp_[k_safe]                                                             faster.cpp:474-475
+ *   sg_safe_.setX0(R); setXf(M); setPolytopes(safe corridor); setForceFinalConstraint(false); genNewTraj(); fillX()
+ *                                                                                              faster.cpp:521-537
+ * fq_replan_pairs does that for n_prob corridors at once without a host round trip between the sweeps: the selection
+ * (first feasible factor, then minimum cost: solverGurobi.cpp:445-472), the sample R of fillX (:122-168), the safe
+ * sweep's getDTInitial(R, M) (:659-759) and its time allocations factor * max(dt_initial, 2 DC) (:494-497) are all
+ * computed on the device.  k_safe = min(n - 1, (int)(r_fraction * n)), n = resetX's sample count (:382-388), stands in
+ * for findIndexR (faster.cpp:173-216), which needs the planner's map.  A corridor whose whole sweep finds nothing gets
+ * no safe sweep: all its safe candidates are "not solved".
+ *
+ * Candidates of corridor j: whole (factors_whole[f], sigmas_whole[s]), index f * n_sig_whole + s; safe likewise. */
+typedef struct fq_pair_result
+{
+  int whole_dt_index, whole_sigma_index;   /* winner of the whole sweep (-1, -1: none)                              */
+  int safe_dt_index, safe_sigma_index;     /* winner of the safe sweep                                               */
+  double whole_cost, safe_cost;            /* +inf: none                                                             */
+  double whole_dt, safe_dt;                /* winning time allocations (NaN: none)                                   */
+  double whole_dt_base, safe_dt_base;      /* max(getDTInitial, 2 DC) of the two sweeps, as computed on the device   */
+  int n_samples_whole, k_safe;             /* resetX count of the whole winner; index of R among its samples         */
+  double R[9];                             /* pos vel accel of R = start state of the safe sweep (NaN: none)         */
+} fq_pair_result;
+
+typedef struct fq_pair_args
+{
+  int n_prob;                              /* corridors = replans                                                    */
+  int N_whole, N_safe;                     /* segments (faster.yaml N_whole, N_safe)                                 */
+  double DC;                               /* setDC: sampling period of fillX, floor 2 DC of findDT                  */
+  double r_fraction;                       /* where R sits on the whole trajectory, in [0, 1]                        */
+  const double* x0;                        /* n_prob x 9: A (pos vel accel)            setX0, faster.cpp:406         */
+  const double* xf_whole;                  /* n_prob x 9: E                            setXf, faster.cpp:407         */
+  const double* xf_safe;                   /* n_prob x 9: M                            setXf, faster.cpp:522         */
+  const double* lim;                       /* n_prob x 3: v_max a_max j_max            setBounds                     */
+  const int* poly_ofs_whole;               /* corridors in the CSR layout of fq_solve_multi    faster.cpp:408        */
+  const int* face_ofs_whole;
+  const double* Ab_whole;
+  const int* poly_ofs_safe;                /*                                                  faster.cpp:523        */
+  const int* face_ofs_safe;
+  const double* Ab_safe;
+  int n_fac_whole;  const double* factors_whole;   /* ascending factors of the whole sweep (solverGurobi.cpp:445-446) */
+  int n_sig_whole;  const uint8_t* sigmas_whole;   /* n_sig_whole x N_whole assignments                               */
+  int n_fac_safe;   const double* factors_safe;
+  int n_sig_safe;   const uint8_t* sigmas_safe;    /* n_sig_safe x N_safe                                             */
+  uint8_t* feasible_whole;  double* cost_whole;    /* out, n_prob x n_fac_whole x n_sig_whole each; may be NULL       */
+  uint8_t* feasible_safe;   double* cost_safe;     /* out, n_prob x n_fac_safe x n_sig_safe each; may be NULL         */
+  double* coeffs_whole;                    /* out, n_prob x N_whole x 12 (winners, x[t][i] order); may be NULL       */
+  double* coeffs_safe;                     /* out, n_prob x N_safe x 12; may be NULL                                 */
+  fq_pair_result* results;                 /* out, n_prob                                                            */
+  /* fq_replan_pairs_dev only (the library cannot read device arrays): largest number of Ab rows of one corridor and
+   * of one polytope, whole and safe */
+  int max_faces_whole, max_poly_faces_whole, max_faces_safe, max_poly_faces_safe;
+} fq_pair_args;
+
+/* HOST pointers everywhere; blocks until the results are in the caller's arrays.  Returns 0 or FQ_E_*. */
+int fq_replan_pairs(fq_ctx* ctx, const fq_pair_args* args);
+/* The same, returning once everything is enqueued; results are valid after fq_wait(ctx).  Arrays must stay alive. */
+int fq_replan_pairs_async(fq_ctx* ctx, const fq_pair_args* args);
+/* DEVICE pointers everywhere (the struct itself lives on the host); enqueues on `stream` (NULL: the context's) and
+ * returns without synchronising.  One chain per context may be in flight on a given stream order: calls on the same
+ * stream are ordered and may follow each other freely; use one context per concurrently used stream (the chain keeps
+ * its intermediate arrays in the context).  With a communicator attached (fq_comm_init / fq_create_multi) and
+ * `results_all` != NULL the chain ends with the path's one collective: an all-gather of the n_prob result records of
+ * every rank into results_all[world x n_prob] (device). */
+int fq_replan_pairs_dev(fq_ctx* ctx, const fq_pair_args* args, fq_pair_result* results_all, void* stream);
+
+/* ---- several GPUs behind the boundary ---------------------------------------------------------
+ *
+ * Candidates of different corridors are independent, so a batch is sharded BY CORRIDOR: contiguous blocks of problems
+ * per GPU (fq_shard_range), no data-path communication while solving.  The path's one exchange is an all-gather of the
+ * per-corridor winners of the genNewTraj selection (solverGurobi.cpp:445-472) -- a few hundred bytes per corridor, not the
+ * per-candidate costs -- with NCCL, the communicator living inside the context.  Nothing like this exists in the
+ * reference (one process, one CPU solver per trajectory kind: faster.hpp:74-75); the entry points below are what a
+ * planner that evaluates many corridors per cycle would bind.  NCCL is loaded at run time (libnccl.so.2; the
+ * environment variable FQ_NCCL_LIB overrides); single-GPU use never touches it.
+ *
+ * One process, n_gpus devices (devices == NULL: 0..n_gpus-1).  The returned context is the context of devices[0] for
+ * every single-GPU entry point, and a GROUP for fq_replan_pairs / fq_replan_pairs_async / fq_solve_multi_sharded, which
+ * spread the corridors over all its devices. */
+int fq_create_multi(fq_ctx** out, int n_gpus, const int* devices);
+/* One process per GPU: rank 0 obtains an id (128 bytes), the launcher distributes it (torch.distributed, MPI, a file),
+ * every rank attaches its own context.  Afterwards fq_replan_pairs / fq_solve_multi_sharded on that context solve the
+ * rank's shard of the (identical) description every rank passes, and fq_replan_pairs_dev / fq_allgather_dev exchange
+ * device-resident results. */
+int fq_comm_unique_id(void* id128);
+int fq_comm_init(fq_ctx* ctx, const void* id128, int rank, int world);
+int fq_comm_info(const fq_ctx* ctx, int* rank, int* world, int* nccl_version);
+/* All-gather of `bytes` bytes per rank between device buffers on `stream` (NULL: the context's), rank order.  A context
+ * without communicator copies (world of one). */
+int fq_allgather_dev(fq_ctx* ctx, const void* d_send, void* d_recv, long bytes, void* stream);
+/* The partition rule: problems [*lo, *hi) belong to `rank`; balanced by candidate count (cand_ofs[n_prob+1], or NULL for
+ * equal problem counts).  Pure host code. */
+int fq_shard_range(int n_prob, const int* cand_ofs, int rank, int world, int* lo, int* hi);
+/* fq_solve_multi on a multi-GPU context (group: all problems solved by this process, spread over its GPUs; rank context:
+ * this rank's shard only, `feasible`/`cost` of other shards stay untouched) plus, for EVERY problem on EVERY rank, the
+ * winner of the genNewTraj selection: win_idx[j] = candidate index relative to cand_ofs[j] (-1: none feasible) of the
+ * feasible candidate with the smallest dt, then the smallest cost; win_cost[j] its cost (+inf: none).  HOST pointers. */
+int fq_solve_multi_sharded(fq_ctx* ctx, int N, int force_final, int n_prob, const double* x0, const double* xf,
+                           const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab,
+                           const int* cand_ofs, const double* dt, const uint8_t* sigma, uint8_t* feasible, double* cost,
+                           int* win_idx, double* win_cost);
 
 /* ---- host-side helpers (no GPU needed) ------------------------------------------------------------- */
 

@@ -40,7 +40,9 @@
 #define FQO_MAXN 16
 #define FQO_NV (3 * FQO_MAXN)          /* jerk variables            */
 #define FQO_NZ (12 * FQO_MAXN)         /* spline coefficients       */
-#define FQO_TOL 1e-8                   /* row violation tolerance (row units: m, m/s, m/s2, m/s3) */
+static double g_row_tol = 1e-8;        /* row violation tolerance (row units: m, m/s, m/s2, m/s3); mirrors the
+                                          product's option "row_tol_1e9" (set before a batch, read by the workers)  */
+#define FQO_TOL g_row_tol
 #define FQO_EPS_DEP 1e-18              /* squared sine below which a normal counts as dependent   */
 #define FQO_MAX_ITER 2000
 
@@ -868,3 +870,8 @@ void fqo_fill_x(int N, const double* coeffs, double dt, double DC, int n_samples
 }
 
 int fqo_abi_version(void) { return 1; }
+
+/* row tolerance of every later solve (default 1e-8; Gurobi's FeasibilityTol default is 1e-6, solverGurobi.cpp:479-487
+ * sets no tolerance parameter) */
+void fqo_set_row_tol(double tol) { if (tol >= 0) g_row_tol = tol; }
+double fqo_get_row_tol(void) { return g_row_tol; }

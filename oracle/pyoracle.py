@@ -35,8 +35,20 @@ def lib():
         L.fqo_num_samples.argtypes = [C.c_int, C.c_double, C.c_double]
         L.fqo_fill_x.restype = None
         L.fqo_fill_x.argtypes = [C.c_int, _d, C.c_double, C.c_double, C.c_int, _d]
+        L.fqo_set_row_tol.restype = None
+        L.fqo_set_row_tol.argtypes = [C.c_double]
+        L.fqo_get_row_tol.restype = C.c_double
         _lib = L
     return _lib
+
+
+def set_row_tol(tol):
+    """Row tolerance of every later solve (mirrors the product's fq_set_option("row_tol_1e9", ...))."""
+    lib().fqo_set_row_tol(float(tol))
+
+
+def get_row_tol():
+    return lib().fqo_get_row_tol()
 
 
 def pack_polys(polys):
