@@ -103,6 +103,7 @@ extern "C" void fq_destroy(fq_ctx* ctx)
   ctx->d_in.release(); ctx->d_out.release(); ctx->d_bnb.release(); ctx->d_pair.release(); ctx->d_pair_io.release();
   ctx->h_in.release(); ctx->h_out.release();
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_memo) cudaFree(ctx->d_memo);
   if (ctx->ev_head) cudaEventDestroy(ctx->ev_head);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -115,6 +116,7 @@ extern "C" int fq_set_option(fq_ctx* ctx, const char* key, int value)
   if (std::string(key) == "force_generic_kernel") { ctx->force_generic = value != 0; return 0; }
   if (std::string(key) == "throughput_slices") { ctx->throughput_slices = value > 0 && value <= 64 ? value : 0; return 0; }
   if (std::string(key) == "max_faces_per_polytope") { ctx->max_poly_faces_hint = value > 0 ? value : 0; return 0; }
+  if (std::string(key) == "cert_memo") { ctx->cert_memo = value != 0; return 0; }
   if (std::string(key) == "row_tol_1e9")
   { // row tolerance in units of 1e-9 (10 = the default 1e-8, 1000 = Gurobi's default FeasibilityTol 1e-6); >= 0
     if (value < 0 || value > 1000000) return fail(ctx, FQ_E_ARG, "row_tol_1e9 out of range (0..1000000)");
@@ -153,7 +155,29 @@ int fq_launch_solve_ctx(fq_ctx* ctx, int N, int force_final, int n_prob, const d
     ctx->counters_cap = n_prob + n_prob / 2;
     FQ_CUDA(cudaMalloc(&ctx->d_counters, sizeof(int) * (size_t)kCounterSlots * ctx->counters_cap));
   }
-  int* counters = ctx->d_counters + (size_t)(ctx->counters_pos++ % kCounterSlots) * ctx->counters_cap;
+  const unsigned slot = ctx->counters_pos++ % kCounterSlots;
+  int* counters = ctx->d_counters + (size_t)slot * ctx->counters_cap;
+  a.memo = nullptr; a.memo_salt = 0;
+#if FQ_CERT_MEMO
+  if (ctx->cert_memo && n_prob <= kFqMemoProbs && max_cand >= 32)
+  { // infeasibility certificates shared between the candidates of a problem (fq_kernels_t.cuh); entries of earlier
+    // launches are recognised by their salt, so nothing has to be cleared per launch
+    const size_t per_slot = (size_t)kFqMemoProbs * FQ_MEMO_NB * FQ_MEMO_BE;
+    if (!ctx->d_memo)
+    {
+      FQ_CUDA(cudaMalloc(&ctx->d_memo, sizeof(FqMemoEntry) * per_slot * kCounterSlots));
+      FQ_CUDA(cudaMemset(ctx->d_memo, 0, sizeof(FqMemoEntry) * per_slot * kCounterSlots));
+    }
+    if (++ctx->memo_salt == 0)
+    { // 2^32 launches later: start over with a clean table
+      FQ_CUDA(cudaDeviceSynchronize());
+      FQ_CUDA(cudaMemset(ctx->d_memo, 0, sizeof(FqMemoEntry) * per_slot * kCounterSlots));
+      ctx->memo_salt = 1;
+    }
+    a.memo = ctx->d_memo + per_slot * slot;
+    a.memo_salt = ctx->memo_salt;
+  }
+#endif
   FQ_CUDA(fq_launch_solve(a, max_cand, stream, counters, ctx->sm_count, env_generic || ctx->force_generic));
   return 0;
 }
@@ -798,6 +822,7 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
     L.k.poly_ofs = (const int*)(db + opo); L.k.face_ofs = (const int*)(db + ofo); L.k.Ab = (const double*)(db + oAb);
     L.k.max_faces = n_face; L.k.item_cap = N * max_pf; L.k.cand_ofs = nullptr; L.k.dt = nullptr; L.k.sigma = nullptr;
     L.k.feasible = nullptr; L.k.cost = nullptr; L.k.coeffs = nullptr; L.k.iters = nullptr; L.k.row_tol = ctx->row_tol;
+    L.k.memo = nullptr; L.k.memo_salt = 0;
     L.n_dt = n_dt; L.P = P; L.dts = (const double*)(db + odts); L.roots = (const int*)(db + oroot);
     L.incumbent = (unsigned long long*)(db + oinc); L.leaves = db + oleaf; L.n_leaves = (int*)(db + ocnt) + 1;
     L.leaf_cap = leaf_cap; L.flags = (int*)(db + ocnt) + 2; L.n_children = (int*)(db + ocnt); L.cap = cap;

@@ -54,7 +54,24 @@ struct FqKernelArgs
   double* coeffs;        // n_cand x N x 12 or nullptr
   int32_t* iters;        // or nullptr
   double row_tol;        // absolute row tolerance (default FQ_ROW_TOL; option "row_tol_1e9")
+  // infeasibility-certificate memo of this launch (fq_kernels_t.cuh), or nullptr: n_prob x FQ_MEMO_NB x FQ_MEMO_BE entries
+  struct FqMemoEntry* memo;
+  unsigned memo_salt;    // unique per launch of a context: entries carrying another salt are stale
 };
+
+// One shared infeasibility certificate: "at time allocation dt (bit pattern), the rows of the segments in `mask` with the
+// polytopes `sigpack` (4 bits per segment) have no common point with the box rows".  w0 = salt << 32 | mask << 16 | count
+// slot + 1; written last, after a fence.
+struct FqMemoEntry
+{
+  unsigned long long w0, dt_bits, sigpack;
+};
+#define FQ_MEMO_NB 16         // buckets per problem (hash of dt)
+#define FQ_MEMO_BE 16         // entries per bucket: one per lane of a half warp
+#ifndef FQ_CERT_MEMO
+#define FQ_CERT_MEMO 1        // 0 compiles the memo out (A/B runs)
+#endif
+#define FQ_MEMO_MARGIN 1e-5   // certificates are recorded only when the violation exceeds this x (1 + sum |multipliers|)
 
 struct FqSelectArgs
 {

@@ -151,9 +151,9 @@ __device__ __forceinline__ void update_Y(const WarpState<D>& m, const double* __
 }
 
 // remove active element l (0 <= l < q); lam / rdinv are per-lane register slots
-template <class D>
+template <class D, bool CERT>
 __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l, int q, double (&lam)[D::SLOTS],
-                                         double (&rdinv)[D::SLOTS])
+                                         double (&rdinv)[D::SLOTS], int (&aseg)[D::SLOTS])
 {
   constexpr int LD = D::LD;
   double dg[D::SLOTS];
@@ -204,6 +204,23 @@ __device__ __forceinline__ void drop_row(const WarpState<D>& m, int lane, int l,
     {
       const int k = lane + 32 * s;
       if (k >= l && k < q - 1) lam[s] = nxt[s];
+    }
+    if constexpr (CERT)
+    { // the segment tags of the active rows move with the multipliers
+      int nx[D::SLOTS];
+#pragma unroll
+      for (int s = 0; s < D::SLOTS; s++)
+      {
+        const int same = __shfl_sync(FULL, aseg[s], (lane + 1) & 31);
+        const int wrap = (s + 1 < D::SLOTS) ? __shfl_sync(FULL, aseg[(s + 1 < D::SLOTS) ? s + 1 : s], 0) : 0;
+        nx[s] = lane == 31 ? wrap : same;
+      }
+#pragma unroll
+      for (int s = 0; s < D::SLOTS; s++)
+      {
+        const int k = lane + 32 * s;
+        if (k >= l && k < q - 1) aseg[s] = nx[s];
+      }
     }
   }
   __syncwarp();
@@ -347,18 +364,23 @@ __device__ __forceinline__ int build_items(const WarpState<D>& m, const int* __r
 // cannot be reached (0) or the iteration cap / a NaN is hit (-1).  Enabled rows = box rows + the `total_rows` items of
 // m.items.  Used by the fixed-assignment solve below and by the branch-and-bound node solve (fq_bnb.cuh), which enters
 // with a parent's factorisation instead of the identity.
-template <class D>
+// CERT: also keep, per active row, the segment it belongs to (0 = box row) and, when the iteration ends "infeasible" with
+// a violation well beyond the tolerance band, return in `cert_mask` the set of segments whose rows (together with box rows)
+// form the Farkas certificate: the entering row and the active rows with a negative multiplier r_k (g_e = sum r_k n_k,
+// r <= 0, active rows tight, row e violated => no point satisfies them all).  cert_mask < 0: no certificate recorded.
+template <class D, bool CERT = false>
 __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __restrict__ TZ, const double* __restrict__ SY,
                                        const double* __restrict__ sAb, const double (&Yeq)[D::RPL][3],
                                        const double (&bthr)[D::RPL], int lane, int total_rows, double inv1, double inv2,
                                        double inv3, double lim0, double lim1, double lim2, double row_tol,
                                        double (&lam)[D::SLOTS], double (&rdinv)[D::SLOTS], int& q, int& it, int bkey,
-                                       unsigned bcode)
+                                       unsigned bcode, int* cert_mask = nullptr)
 {
   constexpr int N = D::N, NZ = D::NZ, NW = D::NW, NYP = D::NYP, LD = D::LD, SLOTS = D::SLOTS;
   double r[SLOTS], z[SLOTS], dreg[SLOTS];
+  int aseg[SLOTS];
 #pragma unroll
-  for (int s = 0; s < SLOTS; s++) { r[s] = 0; z[s] = 0; dreg[s] = 0; }
+  for (int s = 0; s < SLOTS; s++) { r[s] = 0; z[s] = 0; dreg[s] = 0; aseg[s] = 0; }
   int status = -2;
   while (status == -2)
   {
@@ -385,7 +407,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
     const int src = __ffs(__ballot_sync(FULL, key == mk)) - 1;
     const unsigned code = __shfl_sync(FULL, bcode, src);
     // ---- decode the chosen row: Y row y, weights (w0,w1,w2), right-hand side h
-    int y;
+    int y, eseg = 0;
     double w0 = 0, w1 = 0, w2 = 0, h;
     if (code & BOX_FLAG)
     {
@@ -401,6 +423,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
     {
       const unsigned item = m.items[code];
       const int t = item >> 12, gf = item & 0x7ff;
+      eseg = t + 1;
       w0 = sAb[4 * gf]; w1 = sAb[4 * gf + 1]; w2 = sAb[4 * gf + 2];
       const double hb = sAb[4 * gf + 3];            // b + tol
       h = hb - row_tol;
@@ -589,7 +612,25 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
         l = __shfl_sync(FULL, bk, s2);
       }
       const double t2 = dep ? INFINITY : viol * rzz;
-      if (t1 == INFINITY && t2 == INFINITY) { status = 0; break; }
+      if (t1 == INFINITY && t2 == INFINITY)
+      {
+        status = 0;
+        if constexpr (CERT)
+        {
+          double sr = 0;
+          unsigned mk2 = eseg ? 1u << (eseg - 1) : 0u;
+#pragma unroll
+          for (int s = 0; s < SLOTS; s++)
+          {
+            const int k = lane + 32 * s;
+            if (k < q && r[s] < 0) { sr -= r[s]; if (aseg[s]) mk2 |= 1u << (aseg[s] - 1); }
+          }
+          sr = warp_sum(sr);
+          mk2 = __reduce_or_sync(FULL, mk2);
+          *cert_mask = viol > FQ_MEMO_MARGIN * (1.0 + sr) ? (int)mk2 : -1;
+        }
+        break;
+      }
       if (t2 <= t1)
       { // ---- full step: the row becomes active; new basis vector = normalised residual of g
         const double nrm = zz * rn;
@@ -603,7 +644,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
             m.J[i * LD + q] = -z[s] * rn;
           }
           if (i < q) { lam[s] = fma(-t2, r[s], lam[s]); m.R[D::ri(i, q)] = dreg[s]; }
-          if (i == q) { lam[s] = lam_p + t2; rdinv[s] = rn; m.R[D::ri(q, q)] = nrm; }
+          if (i == q) { lam[s] = lam_p + t2; rdinv[s] = rn; m.R[D::ri(q, q)] = nrm; if constexpr (CERT) aseg[s] = eseg; }
         }
         q++;
         __syncwarp();
@@ -622,7 +663,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
       }
       lam_p += t1;
       __syncwarp();
-      drop_row<D>(m, lane, l, q, lam, rdinv);
+      drop_row<D, CERT>(m, lane, l, q, lam, rdinv, aseg);
       q--;
       if (!dep)
       {
@@ -634,6 +675,34 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
   }
 
   return status;
+}
+
+// ---- infeasibility-certificate memo (FqMemoEntry, fq_kernels.cuh) ---------------------------------------------------
+// When gi_loop ends "infeasible", the entering row e and the active rows k with r_k < 0 form a Farkas certificate that
+// does not depend on the candidate's other rows: every candidate of the same problem with the same dt and the same
+// polytope on the segments those rows belong to contains the same rows (box rows are common to all) and is infeasible
+// too.  The ascending time-allocation sweep of genNewTraj starts at an optimistic dt by design (solverGurobi.cpp:445-446),
+// so whole runs of candidates are refuted by the |v|,|a|,|j| boxes alone or by the first segments' rows; they are
+// answered from the memo instead of being re-proved.  Flags stay exact: only proofs are shared, and only those whose
+// violation is far outside the tolerance band (FQ_MEMO_MARGIN).
+__device__ __forceinline__ int memo_bucket(unsigned long long dtb)
+{
+  return (int)((dtb * 0x9E3779B97F4A7C15ull) >> 40) & (FQ_MEMO_NB - 1);
+}
+__device__ __forceinline__ unsigned long long memo_sigpack(int lane, int N, int p)
+{ // 4 bits per segment
+  unsigned lo = 0, hi = 0;
+  if (lane < N) { if (lane < 8) lo = (unsigned)p << (4 * lane); else hi = (unsigned)p << (4 * (lane - 8)); }
+  lo = __reduce_or_sync(FULL, lo);
+  hi = __reduce_or_sync(FULL, hi);
+  return (unsigned long long)hi << 32 | lo;
+}
+__device__ __forceinline__ unsigned long long memo_nibbles(unsigned mask)
+{ // bit t of mask -> nibble t = 0xF
+  unsigned long long r = 0;
+#pragma unroll
+  for (int t = 0; t < 16; t++) r |= (unsigned long long)((mask >> t) & 1u) * (0xfull << (4 * t));
+  return r;
 }
 
 template <class D>
@@ -683,6 +752,41 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
       p = a.sigma[(size_t)cand * N + lane];
       if (p >= P) p = P - 1;
     }
+#if FQ_CERT_MEMO
+    // ---- has another candidate of this problem already proved these rows infeasible at this dt?  (see memo_insert)
+    if (a.memo && P <= 16)
+    {
+      const unsigned long long dtb = (unsigned long long)__double_as_longlong(dt);
+      const unsigned long long sigpack = memo_sigpack(lane, N, p);
+      const FqMemoEntry* e = a.memo + ((size_t)prob * FQ_MEMO_NB + memo_bucket(dtb)) * FQ_MEMO_BE;
+      bool hit = false;
+      if (lane < FQ_MEMO_BE)
+      {
+        const unsigned long long w0 = *reinterpret_cast<const volatile unsigned long long*>(&e[lane].w0);
+        if ((unsigned)(w0 >> 32) == a.memo_salt && (w0 & 0xffffu) != 0)
+        {
+          __threadfence();                               // the entry's other words were written before w0
+          const unsigned long long d = *reinterpret_cast<const volatile unsigned long long*>(&e[lane].dt_bits);
+          const unsigned long long sp = *reinterpret_cast<const volatile unsigned long long*>(&e[lane].sigpack);
+          __threadfence();
+          const unsigned long long w0b = *reinterpret_cast<const volatile unsigned long long*>(&e[lane].w0);
+          hit = w0b == w0 && d == dtb && ((sp ^ sigpack) & memo_nibbles((unsigned)(w0 >> 16) & 0xffffu)) == 0;
+        }
+      }
+      if (__any_sync(FULL, hit))
+      { // same rows, same dt: infeasible, by the recorded certificate (iters = 0 marks the shortcut)
+        if (lane == 0)
+        {
+          a.feasible[cand] = 0;
+          a.cost[cand] = INFINITY;
+          if (a.iters) a.iters[cand] = 0;
+        }
+        if (a.coeffs)
+          for (int idx = lane; idx < 12 * N; idx += 32) a.coeffs[(size_t)cand * N * 12 + idx] = 0.0;
+        return;
+      }
+    }
+#endif
     total_rows = build_items<D>(m, sfo, seg_ofs, lane, N, p, a.item_cap);
     if (total_rows < 0)
     { // the row list does not fit: report "not solved" (iters = -2 marks the cause)
@@ -713,8 +817,38 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
   int bkey = 0;
   unsigned bcode = 0;
   update_Y<D, true>(m, TZ, Yeq, bthr, SY, lane, bkey, bcode);
+#if FQ_CERT_MEMO
+  int cert = -1;
+  const int status = gi_loop<D, true>(m, TZ, SY, sAb, Yeq, bthr, lane, total_rows, inv1, inv2, inv3, lim0, lim1, lim2, a.row_tol,
+                                      lam, rdinv, q, it, bkey, bcode, &cert);
+  if (status == 0 && cert >= 0 && a.memo && P > 0 && P <= 16)
+  { // share the proof with the problem's other candidates: same dt + same polytopes on the certificate's segments
+    int p = 0;
+    if (lane < N) { p = a.sigma[(size_t)cand * N + lane]; if (p >= P) p = P - 1; }
+    const unsigned long long dtb = (unsigned long long)__double_as_longlong(dt);
+    const unsigned long long sigpack = memo_sigpack(lane, N, p);
+    if (lane == 0)
+    {
+      FqMemoEntry* e = a.memo + ((size_t)prob * FQ_MEMO_NB + memo_bucket(dtb)) * FQ_MEMO_BE;
+      // slot = first entry of the bucket not yet taken in this launch (the low 16 bits of w0 hold slot + 1)
+      for (int i = 0; i < FQ_MEMO_BE; i++)
+      {
+        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&e[i].w0);
+        if ((unsigned)(cur >> 32) == a.memo_salt) continue;                 // taken (or being written) in this launch
+        const unsigned long long claim = (unsigned long long)a.memo_salt << 32;      // taken, not yet valid (count field 0)
+        if (atomicCAS(&e[i].w0, cur, claim) != cur) continue;
+        __threadfence();
+        e[i].dt_bits = dtb; e[i].sigpack = sigpack;
+        __threadfence();
+        *reinterpret_cast<volatile unsigned long long*>(&e[i].w0) = claim | ((unsigned long long)(cert & 0xffff) << 16) | (unsigned)(i + 1);
+        break;
+      }
+    }
+  }
+#else
   const int status = gi_loop<D>(m, TZ, SY, sAb, Yeq, bthr, lane, total_rows, inv1, inv2, inv3, lim0, lim1, lim2, a.row_tol,
                                 lam, rdinv, q, it, bkey, bcode);
+#endif
 
   // ================= outputs =================
   double cp = 0;

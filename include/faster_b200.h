@@ -56,7 +56,10 @@ const char* fq_last_error(const fq_ctx* ctx);   /* ctx may be NULL: last creatio
  * default: 4, or 2 for fq_solve_multi_async): how many launches a large host batch is cut into (upload / solve / download of consecutive slices
  * overlap on two streams).  "max_faces_per_polytope": see fq_solve_multi_dev.  "row_tol_1e9" (0..1000000): the absolute row
  * tolerance of every later solve of the context in units of 1e-9 -- 10 is the default FQ_ROW_TOL = 1e-8, 1000 is Gurobi's
- * default FeasibilityTol 1e-6 (the reference sets no tolerance parameter, solverGurobi.cpp:479-487).  Returns 0 or FQ_E_ARG. */
+ * default FeasibilityTol 1e-6 (the reference sets no tolerance parameter, solverGurobi.cpp:479-487).  "cert_memo" (0/1, default 1):
+ * candidates of one problem share their infeasibility proofs (a candidate whose dt and polytopes on the proof's segments
+ * match a recorded Farkas certificate is answered without a solve; same flags, iters = 0 marks them).
+ * Returns 0 or FQ_E_ARG. */
 int fq_set_option(fq_ctx* ctx, const char* key, int value);
 
 /* One corridor problem, n_cand candidates (dt[i], sigma[i*N .. i*N+N-1]); HOST pointers.

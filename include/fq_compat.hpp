@@ -7,6 +7,12 @@
 #include <cstddef>
 #include <vector>
 
+#if __has_include(<Eigen/Dense>)
+// Eigen is present but DecompUtil is not: the look-alikes below are expressed with the real Eigen types
+#include <Eigen/Dense>
+#include <Eigen/StdVector>
+#define FQ_COMPAT_HAVE_EIGEN 1
+#else
 namespace Eigen
 {
 struct Vector3d
@@ -28,6 +34,13 @@ struct Vector3d
   const Vector3d& transpose() const { return *this; }
 };
 }  // namespace Eigen
+#endif
+
+// vec_Vecf<N> of DecompUtil (decomp_basis/data_type.h:50-80): a vector of N-dimensional points
+template <int N>
+using Vecf = Eigen::Vector3d;
+template <int N>
+using vec_Vecf = std::vector<Vecf<N>>;
 
 // F x 3 matrix / F vector with the accessors the solver needs (rows(), (i,j), (i))
 struct FqMatX3

@@ -23,9 +23,9 @@
 #endif
 
 #if __has_include(<decomp_geometry/polyhedron.h>)
-#include <decomp_geometry/polyhedron.h>
-#elif !__has_include(<Eigen/Dense>)
-#include "fq_compat.hpp"
+#include <decomp_geometry/polyhedron.h>          // the reference's LinearConstraint3D, vec_Vecf (DecompUtil)
+#else
+#include "fq_compat.hpp"                         // look-alikes (adapts to Eigen when only Eigen is present)
 #endif
 
 #include <algorithm>
@@ -78,7 +78,13 @@ public:
   void setThreads(int) {}                                                        // :479-482 (Gurobi threads: n/a)
   void setWMax(double w) { w_max_ = w; }                                         // :489-492
   void setMode(int mode) { mode_ = mode; }                                       // :65-68
-  void setDevice(int device) { device_ = device; }                               // additive: CUDA device index
+  // declared in the reference (solverGurobi.hpp:100) but never defined there; kept so that code naming it still compiles
+  void setDistances(vec_Vecf<3>& samples, std::vector<double> dist_near_obs) { (void)samples; (void)dist_near_obs; }
+  void setDevice(int device) { device_ = device; devices_.clear(); releaseContext(); }   // additive: CUDA device index
+  // additive: several GPUs for the batch entry points (fq_create_multi: the corridors of a batch are spread over the
+  // devices, NCCL all-gather of the winners inside the library); genNewTraj() itself is one corridor and uses devices[0]
+  void setDevices(const std::vector<int>& devices) { devices_ = devices; if (!devices.empty()) device_ = devices[0]; releaseContext(); }
+  fq_ctx* context() { return ensureContext() ? ctx_ : nullptr; }                 // for the batch entry points of faster_b200.h
   // Which interval->polytope assignments are evaluated for every time allocation:
   //   ALL       every one of the P^N (the exact MIQP optimum, like Gurobi's branch-and-bound);
   //   MONOTONE  the non-decreasing ones only, C(N+P-1, P-1) (identical genNewTraj results in 960/960 measured sweeps,
@@ -89,7 +95,8 @@ public:
   //             EXACT beyond -- i.e. always the reference's MIQP optimum.
   void setAssignmentMode(AssignmentMode m, long max_assignments = 16384, long auto_all_limit = 4096)
   {
-    amode_ = m; max_sigma_ = max_assignments; auto_all_limit_ = auto_all_limit;
+    amode_ = m; max_sigma_ = max_assignments < 1 ? 1 : max_assignments; auto_all_limit_ = auto_all_limit;
+    sig_N_ = -1;                                   // the cached assignment list depends on all three
   }
 
   void setX0(state& d)                                                           // :298-313
@@ -173,8 +180,9 @@ public:
                              sigmas_.empty() ? nullptr : sigmas_.data(), &dt_idx, &sig_idx, &cost_, coeffs_buf());
       runtime_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       temporal_ = temporal_ + 1;
-      if (rc < 0)
+      if (rc < 0 && !assignments_failed_)
         std::fprintf(stderr, "SolverGurobi(faster_b200): %s\n", ctx_ ? fq_last_error(ctx_) : fq_last_error(nullptr));
+      assignments_failed_ = false;
       if (rc == 1)
       {
         solved = true;
@@ -289,8 +297,10 @@ protected:
   bool ensureContext()
   {
     if (ctx_) return true;
+    if (devices_.size() > 1) return fq_create_multi(&ctx_, (int)devices_.size(), devices_.data()) == 0;
     return fq_create(&ctx_, device_) == 0;
   }
+  void releaseContext() { if (ctx_) { fq_destroy(ctx_); ctx_ = nullptr; } }
   // assignments enumerated for the current (N_, P_): rebuilt only when they change
   bool ensureAssignments()
   {
@@ -309,7 +319,7 @@ protected:
         std::fprintf(stderr, "SolverGurobi(faster_b200): %ld monotone assignments, evaluating an even subset of %ld\n", total, keep);
       for (long k = 0; k < keep; k++)
       {
-        const long src = keep == total ? k : (long)((double)k * (total - 1) / (keep - 1) + 0.5);
+        const long src = (keep == total || keep <= 1) ? k : (long)((double)k * (total - 1) / (keep - 1) + 0.5);
         sigmas_.insert(sigmas_.end(), all.begin() + (size_t)src * N_, all.begin() + (size_t)(src + 1) * N_);
       }
       n_sigma_ = keep;
@@ -317,7 +327,13 @@ protected:
     else
     { // every assignment in P^N (only sensible for small P^N)
       double total = std::pow((double)P_, (double)N_);
-      if (total > (double)max_sigma_) { std::fprintf(stderr, "SolverGurobi(faster_b200): P^N too large for ALL mode\n"); return false; }
+      if (total > (double)max_sigma_)
+      {
+        std::fprintf(stderr, "SolverGurobi(faster_b200): P^N = %.0f assignments exceed max_assignments = %ld in ALL mode (use AUTO or EXACT)\n",
+                     total, max_sigma_);
+        assignments_failed_ = true;
+        return false;
+      }
       std::vector<uint8_t> s(N_, 0);
       for (;;)
       {
@@ -351,6 +367,8 @@ protected:
   AssignmentMode amode_ = AUTO;
   fq_ctx* ctx_ = nullptr;
   int device_ = 0;
+  std::vector<int> devices_;
+  bool assignments_failed_ = false;
   int verbose_ = 0;
   int mode_ = 0;
   bool forceFinalConstraint_ = true;

@@ -38,11 +38,13 @@ def _sub_polys(po_, fo_, Ab, j):
     return [(Ab[fo_[p]:fo_[p + 1], :3], Ab[fo_[p]:fo_[p + 1], 3]) for p in range(po_[j], po_[j + 1])]
 
 
-def replan_pairs(w, threads=1, dt_base_whole=None, dt_base_safe=None):
+def replan_pairs(w, threads=1, dt_base_whole=None, dt_base_safe=None, fast=False):
     """w: dict as faster_b200.capi.make_pair_workload builds.  dt_base_* (optional): use these time-allocation bases (e.g.
     the ones the device computed) instead of the oracle's own getDTInitial, so that a solve comparison is not disturbed
     by a last-bit difference in dt.  -> dict with the fields of fq_pair_result as arrays, per-candidate flags / costs,
-    and the winners' coefficients."""
+    and the winners' coefficients.  fast=True: the sweeps run through the tuned CPU port (oracle/fq_cpu_port.c) instead of
+    the literal restatement (fq_oracle.c): bench.py's CPU arm."""
+    solve_multi = (lambda *a: po.solve_multi_port(*a)[:2]) if fast else po.solve_multi
     n, Nw, Ns, DC = w["n_prob"], w["N_whole"], w["N_safe"], w["DC"]
     fw, fs, sw, ss = w["factors_whole"], w["factors_safe"], w["sigmas_whole"], w["sigmas_safe"]
     out = {}
@@ -51,7 +53,7 @@ def replan_pairs(w, threads=1, dt_base_whole=None, dt_base_safe=None):
     if dt_base_whole is not None:
         dbw = np.asarray(dt_base_whole, float)
     dts, sig, co = _expand(n, fw, sw, dbw)
-    feas_w, cost_w = po.solve_multi(Nw, True, w["x0"], w["xf_whole"], w["lim"], w["poly_ofs_whole"], w["face_ofs_whole"],
+    feas_w, cost_w = solve_multi(Nw, True, w["x0"], w["xf_whole"], w["lim"], w["poly_ofs_whole"], w["face_ofs_whole"],
                                     w["Ab_whole"], co, dts, sig, threads)
     di, si = _select(feas_w, cost_w, n, len(fw), len(sw))
     R = np.full((n, 9), np.nan)
@@ -60,12 +62,21 @@ def replan_pairs(w, threads=1, dt_base_whole=None, dt_base_safe=None):
     coeffs_w = np.zeros((n, Nw, 12))
     wcost = np.full(n, np.inf)
     wdt = np.full(n, np.nan)
+    if fast and (di >= 0).any():
+        # winners' coefficients in one batch through the port (one candidate per corridor)
+        dtw = np.where(di >= 0, np.asarray(fw)[np.maximum(di, 0)] * dbw, 1.0)
+        fwn, cwn, cfw = po.solve_multi_port(Nw, True, w["x0"], w["xf_whole"], w["lim"], w["poly_ofs_whole"], w["face_ofs_whole"],
+                                            w["Ab_whole"], np.arange(n + 1, dtype=np.int32), dtw, sw[np.maximum(si, 0)], threads,
+                                            want_coeffs=True)
     for j in range(n):
         if di[j] < 0:
             continue
         dt = fw[di[j]] * dbw[j]
-        st, c, cf, _ = po.solve_fixed(Nw, w["x0"][j], w["xf_whole"][j], w["lim"][j], dt,
-                                      _sub_polys(w["poly_ofs_whole"], w["face_ofs_whole"], w["Ab_whole"], j), sw[si[j]], True)
+        if fast:
+            st, c, cf = int(fwn[j]), cwn[j], cfw[j]
+        else:
+            st, c, cf, _ = po.solve_fixed(Nw, w["x0"][j], w["xf_whole"][j], w["lim"][j], dt,
+                                          _sub_polys(w["poly_ofs_whole"], w["face_ofs_whole"], w["Ab_whole"], j), sw[si[j]], True)
         assert st == 1
         coeffs_w[j], wcost[j], wdt[j] = cf, c, dt
         X = po.fill_x(Nw, cf, dt, DC)
@@ -98,7 +109,7 @@ def replan_pairs(w, threads=1, dt_base_whole=None, dt_base_safe=None):
             sub_po.append(sub_po[-1] + po_s[j + 1] - po_s[j])
         Ab = np.ascontiguousarray(np.vstack(rows)) if rows else np.zeros((1, 4))
         dts, sig, co = _expand(len(idx), fs, ss, dbs[idx])
-        f, c = po.solve_multi(Ns, False, np.ascontiguousarray(R[idx]), np.ascontiguousarray(w["xf_safe"][idx]),
+        f, c = solve_multi(Ns, False, np.ascontiguousarray(R[idx]), np.ascontiguousarray(w["xf_safe"][idx]),
                               np.ascontiguousarray(w["lim"][idx]), np.array(sub_po, np.int32), np.array(sub_fo, np.int32), Ab,
                               co, dts, sig, threads)
         per = nfs * nss
@@ -106,13 +117,22 @@ def replan_pairs(w, threads=1, dt_base_whole=None, dt_base_safe=None):
             feas_s[j * per:(j + 1) * per] = f[q * per:(q + 1) * per]
             cost_s[j * per:(j + 1) * per] = c[q * per:(q + 1) * per]
         d2, s2 = _select(f, c, len(idx), nfs, nss)
+        if fast and (d2 >= 0).any():
+            dtq = np.where(d2 >= 0, np.asarray(fs)[np.maximum(d2, 0)] * dbs[idx], 1.0)
+            fsn, csn, cfs = po.solve_multi_port(Ns, False, np.ascontiguousarray(R[idx]), np.ascontiguousarray(w["xf_safe"][idx]),
+                                                np.ascontiguousarray(w["lim"][idx]), np.array(sub_po, np.int32), np.array(sub_fo, np.int32),
+                                                Ab, np.arange(len(idx) + 1, dtype=np.int32), dtq, ss[np.maximum(s2, 0)], threads,
+                                                want_coeffs=True)
         for q, j in enumerate(idx):
             if d2[q] < 0:
                 continue
             sdi[j], ssi[j] = d2[q], s2[q]
             dt = fs[d2[q]] * dbs[j]
-            st, cc, cf, _ = po.solve_fixed(Ns, R[j], w["xf_safe"][j], w["lim"][j], dt, _sub_polys(po_s, fo_s, w["Ab_safe"], j),
-                                           ss[s2[q]], False)
+            if fast:
+                st, cc, cf = int(fsn[q]), csn[q], cfs[q]
+            else:
+                st, cc, cf, _ = po.solve_fixed(Ns, R[j], w["xf_safe"][j], w["lim"][j], dt, _sub_polys(po_s, fo_s, w["Ab_safe"], j),
+                                               ss[s2[q]], False)
             assert st == 1
             coeffs_s[j], scost[j], sdt[j] = cf, cc, dt
     out.update(whole_dt_index=di, whole_sigma_index=si, safe_dt_index=sdi, safe_sigma_index=ssi, whole_cost=wcost,
