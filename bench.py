@@ -121,6 +121,20 @@ def make_single(cfg, n_corr, dt_initial):
                 max_faces=int(max(fo[po[j + 1]] - fo[po[j]] for j in range(n_corr))), max_poly_faces=int(np.diff(fo).max()))
 
 
+N_DT, N_SIG, CAND = 16, 64, 1024
+
+
+def make_workload(n_corr, seed0, kind):
+    """Round 1's synthetic "cfg2-pairs" batches (whole: P=3, final position pinned; safe: P=4, free), still used by the
+    stress and modelling tools under tools/: make_single's layout plus the corridor dicts."""
+    from faster_b200 import capi, corridor as cr
+    cfg = dict(SINGLE["cfg2"], seed=seed0) if kind == "whole" else dict(SINGLE["cfg2"], P=4, ff=False, seed=seed0)
+    w = make_single(cfg, n_corr, capi.dt_initial)
+    w["kind"] = kind
+    w["probs"] = [cr.make_corridor(seed0 + c, cfg["P"], cfg["N"], cfg["profile"], cfg["ff"]) for c in range(n_corr)]
+    return w
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     def __init__(self, index):
@@ -254,6 +268,7 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--single-stream", action="store_true", help="all chains on one stream / context (no overlap of consecutive batches)")
     ap.add_argument("--quick", action="store_true", help="profiling runs: main timing only")
+    ap.add_argument("--no-memo", action="store_true", help="A/B: switch the infeasibility-certificate memo off (option cert_memo = 0)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -287,6 +302,9 @@ def main():
     # ---- contexts: two (chains of consecutive batches overlap on two streams), each attached to the communicator
     n_ctx = 1 if args.single_stream else 2
     solvers = [capi.Solver(local) for _ in range(n_ctx)]
+    if args.no_memo:
+        for sv in solvers:
+            sv.set_option("cert_memo", 0)
     if world > 1:
         for k, sv in enumerate(solvers):                     # one communicator per context: collectives of the two streams
             uid = [capi.comm_unique_id() if rank == 0 else None]      # must not share one (NCCL orders per communicator)
@@ -361,6 +379,9 @@ def main():
                   feasible_safe=torch.zeros(nc, dtype=torch.uint8).pin_memory().numpy(), cost_safe=torch.zeros(nc, dtype=torch.float64).pin_memory().numpy())
         host.append((hw, ho))
     e2e_solvers = [capi.Solver(local) for _ in range(2)]     # plain contexts: the e2e leg measures the host path of one GPU
+    if args.no_memo:
+        for sv in e2e_solvers:
+            sv.set_option("cert_memo", 0)
 
     def e2e_passes(n_pass):
         for p in range(n_pass):
@@ -401,7 +422,7 @@ def main():
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": cfg4_config(world, C),
-                "run": {"passes_per_step": inner, "distinct_batches": ring,
+                "run": {"passes_per_step": inner, "distinct_batches": ring, "certificate_memo": not args.no_memo,
                         "streams": "one" if args.single_stream else
                                    "two contexts / streams: the chains of consecutive batches overlap (the tail of one fills with the next)"},
                 "timed_region_s": total_ms * 1e-3,

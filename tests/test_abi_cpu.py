@@ -19,7 +19,7 @@ def test_exports_match_header(built_lib):
     for name in sorted(declared):
         assert hasattr(L, name), "libfaster_b200.so lacks %s" % name
     assert declared == set(capi.EXPORTS)
-    assert L.fq_abi_version() == 1
+    assert L.fq_abi_version() == 2
 
 
 def test_no_gpu_fails_loudly(built_lib):

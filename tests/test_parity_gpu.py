@@ -393,7 +393,8 @@ def test_deferred_host_batches_on_two_contexts(solver):
     deferred one first, and the slice count does not change any bit."""
     import bench
     second = capi.Solver(0)
-    works = [bench.make_workload(32, 4100, "whole"), bench.make_workload(32, 4200, "safe")]   # > 512 KB: throughput path
+    works = [bench.make_single(dict(bench.SINGLE["cfg2"], seed=4100), 32, capi.dt_initial),    # > 512 KB: throughput path
+             bench.make_single(dict(bench.SINGLE["cfg2"], P=4, ff=False, seed=4200), 32, capi.dt_initial)]
     args = [(w["N"], w["ff"], w["x0"], w["xf"], w["lim"], w["poly_ofs"], w["face_ofs"], w["Ab"], w["cand_ofs"], w["dt"], w["sigma"])
             for w in works]
     ref = [solver.solve_multi(*a) for a in args]                              # blocking
@@ -406,7 +407,7 @@ def test_deferred_host_batches_on_two_contexts(solver):
     assert ref[0][0].any() and not ref[0][0].all()
     # a second call on a context with a deferred batch in flight: the first batch's outputs must be complete afterwards
     o1 = solver.solve_multi(*args[0], deferred=True)
-    pb = works[0]["probs"][0]
+    pb = cr.make_corridor(4100, 3, 10, "uav", True)
     g = solver.gen_new_traj(10, pb["x0"], pb["xf"], pb["lim"], pb["polys"], np.arange(1, 11) * 0.3, cr.monotone_sigmas(10, 3), True)
     assert np.array_equal(o1[0], ref[0][0]) and np.array_equal(o1[1], ref[0][1]) and g["dt_index"] >= -1
     for n_slices in (1, 2, 7):
