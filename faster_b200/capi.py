@@ -14,7 +14,7 @@ EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_set
            "fq_solve_multi_async", "fq_wait", "fq_solve_multi_dev", "fq_gen_new_traj", "fq_gen_new_traj_sampled", "fq_gen_new_traj_exact", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
            "fq_monotone_sigmas", "fq_plan_tables", "fq_ellipsoid_decomp", "fq_jps3d_plan", "fq_jps3d_plan_world", "fq_jps3d_rules",
            "fq_replan_pairs", "fq_replan_pairs_async", "fq_replan_pairs_dev", "fq_create_multi", "fq_comm_unique_id", "fq_comm_init",
-           "fq_comm_info", "fq_allgather_dev", "fq_shard_range", "fq_solve_multi_sharded"]
+           "fq_comm_info", "fq_allgather_dev", "fq_shard_range", "fq_solve_multi_sharded", "fq_solve_batch_cert"]
 
 
 class FqError(RuntimeError):
@@ -395,6 +395,24 @@ class Solver:
                                            co.ctypes.data if want_coeffs else None,
                                            it.ctypes.data if want_iters else None))
         return feas, cost, co, it
+
+    def solve_batch_cert(self, N, x0, xf, lim, polys, dts, sigmas, force_final=True):
+        """fq_solve_batch_cert -> (feasible, cost, cert[n, stride]): Farkas certificates of the infeasible candidates."""
+        P, ofs, Ab = pack_polys(polys)
+        dts = _f64(dts)
+        n = dts.size
+        sig = np.ascontiguousarray(np.asarray(sigmas, np.uint8).reshape(n, N)) if P > 0 else np.zeros((n, N), np.uint8)
+        x0, xf, lim = _f64(x0, 9), _f64(xf, 9), _f64(lim, 3)
+        feas = np.zeros(n, np.uint8)
+        cost = np.zeros(n)
+        stride = 4 + 6 * 16
+        cert = np.zeros((n, stride))
+        self._L.fq_solve_batch_cert.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+        self._check(self._L.fq_solve_batch_cert(self._h, int(N), int(bool(force_final)), x0.ctypes.data, xf.ctypes.data, lim.ctypes.data,
+                                                P, ofs.ctypes.data, Ab.ctypes.data, n, dts.ctypes.data, sig.ctypes.data,
+                                                feas.ctypes.data, cost.ctypes.data, cert.ctypes.data, stride))
+        return feas, cost, cert
 
     def solve_multi(self, N, force_final, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dts, sigmas,
                     want_coeffs=False, want_iters=False, out=None, deferred=False):

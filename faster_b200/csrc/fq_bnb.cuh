@@ -94,7 +94,6 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
   bool rows_bad = false;
   {
     const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
-    double2* dst = reinterpret_cast<double2*>(sAb);
     int bad = 0;
     const bool fits = nf >= 0 && nf <= a.max_faces;      // never overrun the staging area: cut the tree instead
     for (int i = threadIdx.x; fits && i < 2 * nf; i += blockDim.x)
@@ -102,7 +101,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
       double2 v = src[i];
       bad |= !(fabs(v.x) < 1e300) || !(fabs(v.y) < 1e300);
       if (i & 1) v.y += a.row_tol;
-      dst[i] = v;
+      fqt::row_store(sAb, i, 2 * a.max_faces, v);
     }
     for (int i = threadIdx.x; i <= P && i < 36; i += blockDim.x) sfo[i] = a.face_ofs[p0 + i] - f0;
     rows_bad = __syncthreads_or(bad) != 0;
@@ -124,6 +123,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? 4 : (N_ <= 15 ? 3 : 2))) f
     m.d = p;   p += NW + 2;
     m.zb = p;  p += NW;
     m.items = reinterpret_cast<unsigned short*>(p);
+    m.half_ofs = 2 * a.max_faces;
     seg_ofs = sfo + 40 + warp * 32;
   }
   // ---- parent

@@ -157,7 +157,7 @@ int fq_launch_solve_ctx(fq_ctx* ctx, int N, int force_final, int n_prob, const d
   }
   const unsigned slot = ctx->counters_pos++ % kCounterSlots;
   int* counters = ctx->d_counters + (size_t)slot * ctx->counters_cap;
-  a.memo = nullptr; a.memo_salt = 0;
+  a.memo = nullptr; a.memo_salt = 0; a.cert = ctx->cert_out; a.cert_stride = ctx->cert_stride;
 #if FQ_CERT_MEMO
   if (ctx->cert_memo && n_prob <= kFqMemoProbs && max_cand >= 32)
   { // infeasibility certificates shared between the candidates of a problem (fq_kernels_t.cuh); entries of earlier
@@ -178,7 +178,7 @@ int fq_launch_solve_ctx(fq_ctx* ctx, int N, int force_final, int n_prob, const d
     a.memo_salt = ctx->memo_salt;
   }
 #endif
-  FQ_CUDA(fq_launch_solve(a, max_cand, stream, counters, ctx->sm_count, env_generic || ctx->force_generic));
+  FQ_CUDA(fq_launch_solve(a, max_cand, stream, counters, ctx->sm_count, env_generic || ctx->force_generic || a.cert != nullptr));
   return 0;
 }
 namespace
@@ -523,6 +523,29 @@ extern "C" int fq_wait(fq_ctx* ctx)
   return settle(ctx);
 }
 
+// fq_solve_batch through the size-generic kernel, which also exports, for every candidate it finds infeasible, the Farkas
+// certificate it stopped on (include/faster_b200.h)
+extern "C" int fq_solve_batch_cert(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf, const double* lim,
+                                   int P, const int* face_ofs, const double* Ab, int n_cand, const double* dt,
+                                   const uint8_t* sigma, uint8_t* feasible, double* cost, double* cert, int cert_stride)
+{
+  if (!ctx) return FQ_E_ARG;
+  if (!cert || cert_stride < 4 + 2 * 3 * FQ_MAX_N || n_cand <= 0) return fq_fail(ctx, FQ_E_ARG, "cert buffer: stride >= 4 + 6 FQ_MAX_N doubles per candidate");
+  if (int rc = fq_settle(ctx)) return rc;
+  FQ_CUDA(cudaSetDevice(ctx->device));
+  FqArena arena;
+  FQ_CUDA(arena.reserve(sizeof(double) * (size_t)cert_stride * n_cand));
+  FQ_CUDA(cudaMemset(arena.p, 0, sizeof(double) * (size_t)cert_stride * n_cand));
+  ctx->cert_out = (double*)arena.p; ctx->cert_stride = cert_stride;
+  const int rc = fq_solve_batch(ctx, N, force_final, x0, xf, lim, P, face_ofs, Ab, n_cand, dt, sigma, feasible, cost, nullptr, nullptr);
+  ctx->cert_out = nullptr; ctx->cert_stride = 0;
+  cudaError_t e = cudaMemcpy(cert, arena.p, sizeof(double) * (size_t)cert_stride * n_cand, cudaMemcpyDeviceToHost);
+  arena.release();
+  if (rc) return rc;
+  FQ_CUDA(e);
+  return 0;
+}
+
 extern "C" int fq_solve_batch(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf,
                               const double* lim, int P, const int* face_ofs, const double* Ab, int n_cand,
                               const double* dt, const uint8_t* sigma, uint8_t* feasible, double* cost,
@@ -822,7 +845,7 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
     L.k.poly_ofs = (const int*)(db + opo); L.k.face_ofs = (const int*)(db + ofo); L.k.Ab = (const double*)(db + oAb);
     L.k.max_faces = n_face; L.k.item_cap = N * max_pf; L.k.cand_ofs = nullptr; L.k.dt = nullptr; L.k.sigma = nullptr;
     L.k.feasible = nullptr; L.k.cost = nullptr; L.k.coeffs = nullptr; L.k.iters = nullptr; L.k.row_tol = ctx->row_tol;
-    L.k.memo = nullptr; L.k.memo_salt = 0;
+    L.k.memo = nullptr; L.k.memo_salt = 0; L.k.cert = nullptr; L.k.cert_stride = 0;
     L.n_dt = n_dt; L.P = P; L.dts = (const double*)(db + odts); L.roots = (const int*)(db + oroot);
     L.incumbent = (unsigned long long*)(db + oinc); L.leaves = db + oleaf; L.n_leaves = (int*)(db + ocnt) + 1;
     L.leaf_cap = leaf_cap; L.flags = (int*)(db + ocnt) + 2; L.n_children = (int*)(db + ocnt); L.cap = cap;

@@ -72,6 +72,8 @@ struct fq_ctx
   FqMemoEntry* d_memo = nullptr;  // ring of infeasibility-certificate memos: one slot per launch in flight (as d_counters)
   unsigned memo_salt = 0;         // launch counter stamped into the memo entries (stale entries carry another value)
   bool cert_memo = true;          // option "cert_memo"
+  double* cert_out = nullptr;     // fq_solve_batch_cert: device buffer the generic kernel writes certificates into
+  int cert_stride = 0;
   // ---- multi-GPU (fq_multi.cu)
   FqComm* comm = nullptr;         // communicator this context belongs to (one process per GPU), or nullptr
   int rank = 0, world = 1;

@@ -40,7 +40,7 @@ __device__ __forceinline__ double warp_min(double v)
 struct WarpMem
 {
   double *J, *R, *Y, *Yeq, *w, *g, *d, *z, *lam, *r, *rdinv, *hdr;
-  int *seg_ofs, *sig;
+  int *seg_ofs, *sig, *act;     // act[k]: id of the k-th active row (certificate export)
 };
 
 __host__ __device__ inline int per_warp_doubles(int nw, int ld, int NY)
@@ -48,7 +48,7 @@ __host__ __device__ inline int per_warp_doubles(int nw, int ld, int NY)
   const int nwp = nw > 0 ? nw : 1;
   return 2 * nwp * ld + 2 * 3 * NY + 7 * nwp + 24;
 }
-__host__ __device__ inline int per_warp_ints() { return 2 * (FQ_MAX_N + 2); }
+__host__ __device__ inline int per_warp_ints() { return 2 * (FQ_MAX_N + 2) + 3 * FQ_MAX_N; }
 
 // Y = Yeq + TZ w
 __device__ __forceinline__ void recompute_Y(const FqKernelArgs& a, const double* TZ, const WarpMem& m, int lane)
@@ -76,9 +76,10 @@ __device__ __forceinline__ void drop_row(const FqKernelArgs& a, const WarpMem& m
   {
     const int k = base + lane;
     double t = 0;
-    if (k < q - 1) t = m.lam[k + 1];
+    int ta = 0;
+    if (k < q - 1) { t = m.lam[k + 1]; ta = m.act[k + 1]; }
     __syncwarp();
-    if (k < q - 1) m.lam[k] = t;
+    if (k < q - 1) { m.lam[k] = t; m.act[k] = ta; }
     __syncwarp();
   }
   __syncwarp();
@@ -185,7 +186,8 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
   {
     // ================= most violated row =================
     double bv = a.row_tol, bw0 = 0, bw1 = 0, bw2 = 0, bh = 0;
-    int by = 0;
+    int by = 0, bid = 0;   // bid: row identity for the certificate export (fq_solve_batch_cert): box rows
+                           // 1000000 + type*10000 + axis*1000 + t*10 + (upper bound ? 1 : 0); corridor rows t*100000 + face*10 + cp
     for (int i = lane; i < 9 * N; i += 32)
     { // |v|,|a|,|j| boxes at segment starts (solverGurobi.cpp:390-407); type 0 v, 1 a, 2 j
       const int type = i / (3 * N), rem = i - type * 3 * N, ax = rem / N, t = rem - ax * N;
@@ -198,6 +200,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
       {
         const double s = val > 0 ? sinv : -sinv;
         bv = viol; by = y; bh = L;
+        bid = 1000000 + type * 10000 + ax * 1000 + t * 10 + (val > 0 ? 1 : 0);
         bw0 = ax == 0 ? s : 0.0; bw1 = ax == 1 ? s : 0.0; bw2 = ax == 2 ? s : 0.0;
       }
     }
@@ -214,7 +217,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
       {
         const int y = ys[k];
         const double v = fma(a01.x, m.Y[y], fma(a01.y, m.Y[NY + y], fma(a23.x, m.Y[2 * NY + y], -a23.y)));
-        if (v > bv) { bv = v; by = y; bw0 = a01.x; bw1 = a01.y; bw2 = a23.x; bh = a23.y; }
+        if (v > bv) { bv = v; by = y; bw0 = a01.x; bw1 = a01.y; bw2 = a23.x; bh = a23.y; bid = t * 100000 + gf * 10 + k; }
       }
     }
     const unsigned key = bv > a.row_tol ? __float_as_uint(fmaxf((float)bv, 1e-30f)) : 0u;
@@ -222,6 +225,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
     if (mk == 0u) { status = 1; break; }
     const int src = __ffs(__ballot_sync(FULL, key == mk)) - 1;
     const int y = __shfl_sync(FULL, by, src);
+    const int eid = __shfl_sync(FULL, bid, src);
     const double w0 = __shfl_sync(FULL, bw0, src), w1 = __shfl_sync(FULL, bw1, src),
                  w2 = __shfl_sync(FULL, bw2, src), h = __shfl_sync(FULL, bh, src);
 
@@ -292,7 +296,18 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
         l = __shfl_sync(FULL, bk, s2);
       }
       const double t2 = dep ? INFINITY : viol / zz;
-      if (t1 == INFINITY && t2 == INFINITY) { status = 0; done = true; break; }
+      if (t1 == INFINITY && t2 == INFINITY)
+      {
+        status = 0; done = true;
+        if (a.cert)
+        { // Farkas certificate: entering row with multiplier 1, active rows with -r_k >= 0 (g_e = sum r_k n_k, r <= 0)
+          double* c = a.cert + (size_t)cand * a.cert_stride;
+          if (lane == 0) { c[0] = (double)(q + 1); c[1] = viol; c[2] = (double)eid; c[3] = 1.0; }
+          for (int k = lane; k < q; k += 32)
+            if (4 + 2 * k + 1 < a.cert_stride) { c[4 + 2 * k] = (double)m.act[k]; c[4 + 2 * k + 1] = -m.r[k]; }
+        }
+        break;
+      }
       if (t2 <= t1)
       { // full step: the row becomes active (Householder update of J2, new column of R)
         for (int j = lane; j < nw; j += 32) m.w[j] = fma(t2, m.z[j], m.w[j]);
@@ -308,7 +323,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
           for (int j = q + 1; j < nw; j++) Ji[j] = fma(-bu, m.d[j], Ji[j]);
         }
         for (int k = lane; k < q; k += 32) m.R[k * ld + q] = m.d[k];
-        if (lane == 0) { m.R[q * ld + q] = -sgn * nrm; m.rdinv[q] = -sgn / nrm; m.lam[q] = lam_p; }
+        if (lane == 0) { m.R[q * ld + q] = -sgn * nrm; m.rdinv[q] = -sgn / nrm; m.lam[q] = lam_p; m.act[q] = eid; }
         q++;
         __syncwarp();
         recompute_Y(a, TZ, m, lane);
@@ -421,7 +436,7 @@ __global__ void __launch_bounds__(W * 32) fq_solve_kernel(const FqKernelArgs a, 
   m.rdinv = p;  p += nwp;
   m.hdr = p;
   int* ip = ibase + warp * per_warp_ints();
-  m.seg_ofs = ip; m.sig = ip + FQ_MAX_N + 2;
+  m.seg_ofs = ip; m.sig = ip + FQ_MAX_N + 2; m.act = ip + 2 * (FQ_MAX_N + 2);
   solve_candidate(a, TZ, T0, sAb, sfo, m, prob, cand, lane, rows_bad);
 }
 

@@ -23,6 +23,10 @@
 #define FQ_WARP_ADOPT 1       // 1: every warp adopts problems and stages polytope rows on its own (no block barriers):
                               // +5 % over packed R alone, +2.5 % net (tools/ab.sh, same box: 53.6 -> 54.95 M pairs/s)
 #endif
+#ifndef FQ_SPLIT_ROWS
+#define FQ_SPLIT_ROWS 0       // 1: staged polytope rows as two arrays of 16-byte halves ([Ax Ay] and [Az b+tol]): both loads of
+                              // the row scan become bank-conflict free (rows 32 bytes apart give a two-way conflict)
+#endif
 #define FQ_EPS_DEP 1e-18      // squared sine below which a new normal counts as dependent on the active set
 #define FQ_ZZ_FLOOR 1e-30
 #define FQ_MAX_ITERS 400
@@ -57,6 +61,9 @@ struct FqKernelArgs
   // infeasibility-certificate memo of this launch (fq_kernels_t.cuh), or nullptr: n_prob x FQ_MEMO_NB x FQ_MEMO_BE entries
   struct FqMemoEntry* memo;
   unsigned memo_salt;    // unique per launch of a context: entries carrying another salt are stale
+  // size-generic kernel only (fq_solve_batch_cert): per infeasible candidate, [n, violation, (row id, multiplier) x n]
+  double* cert;
+  int cert_stride;
 };
 
 // One shared infeasibility certificate: "at time allocation dt (bit pattern), the rows of the segments in `mask` with the

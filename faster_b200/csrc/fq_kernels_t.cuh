@@ -85,6 +85,25 @@ __device__ __forceinline__ double warp_min(double v)
   return v;
 }
 
+// staged polytope rows: row gf = (a01 = [Ax Ay], a23 = [Az b+tol]); interleaved (32-byte rows) or split into two arrays
+// of 16-byte halves `half_ofs` doubles apart (FQ_SPLIT_ROWS; half_ofs = 2 * max_faces)
+__device__ __forceinline__ double2 row_a01(const double* __restrict__ sAb, int gf, int half_ofs)
+{
+  (void)half_ofs;
+  return *reinterpret_cast<const double2*>(sAb + (FQ_SPLIT_ROWS ? 2 : 4) * gf);
+}
+__device__ __forceinline__ double2 row_a23(const double* __restrict__ sAb, int gf, int half_ofs)
+{
+  return *reinterpret_cast<const double2*>(sAb + (FQ_SPLIT_ROWS ? half_ofs + 2 * gf : 4 * gf + 2));
+}
+// staging: double2 number i of the source rows (even: [Ax Ay] of row i/2, odd: [Az b] of row i/2)
+__device__ __forceinline__ void row_store(double* __restrict__ sAb, int i, int half_ofs, double2 v)
+{
+  double2* dst = reinterpret_cast<double2*>(sAb);
+  if (FQ_SPLIT_ROWS) dst[(i & 1) ? (half_ofs >> 1) + (i >> 1) : (i >> 1)] = v;
+  else dst[i] = v;
+}
+
 template <class D>
 struct WarpState
 {
@@ -95,6 +114,7 @@ struct WarpState
   double* d;            // NW
   double* zb;           // NW: scratch for the re-orthogonalisation pass
   unsigned short* items;
+  int half_ofs;         // FQ_SPLIT_ROWS: distance in doubles between the two halves of the staged rows
 };
 
 // Ranking key of a row: hi word of (violation - tol) * S[y] as a signed int, S[y] = 1/|TZ[y]| (distance of the
@@ -389,8 +409,8 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
     {
       const unsigned item = m.items[i];
       const int t = item >> 12, gf = item & 0x7ff;
-      const double2 a01 = *reinterpret_cast<const double2*>(sAb + 4 * gf);
-      const double2 a23 = *reinterpret_cast<const double2*>(sAb + 4 * gf + 2);     // a23.y = b + tol
+      const double2 a01 = row_a01(sAb, gf, m.half_ofs);
+      const double2 a23 = row_a23(sAb, gf, m.half_ofs);                             // a23.y = b + tol
       const double* Y0 = m.Y; const double* Y1 = m.Y + NYP; const double* Y2 = m.Y + 2 * NYP;
       const int y1 = 4 * N + 1 + t, y2 = 5 * N + 1 + t;
       const double u1 = fma(a01.x, Y0[y1], fma(a01.y, Y1[y1], fma(a23.x, Y2[y1], -a23.y))) * SY[y1];
@@ -424,8 +444,9 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
       const unsigned item = m.items[code];
       const int t = item >> 12, gf = item & 0x7ff;
       eseg = t + 1;
-      w0 = sAb[4 * gf]; w1 = sAb[4 * gf + 1]; w2 = sAb[4 * gf + 2];
-      const double hb = sAb[4 * gf + 3];            // b + tol
+      const double2 r01 = row_a01(sAb, gf, m.half_ofs), r23 = row_a23(sAb, gf, m.half_ofs);
+      w0 = r01.x; w1 = r01.y; w2 = r23.x;
+      const double hb = r23.y;                      // b + tol
       h = hb - row_tol;
       const int ys[4] = { 4 * N + 1 + t, 5 * N + 1 + t, t + 1, t };
       y = ys[0];
@@ -932,6 +953,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
     m.d = p;   p += D::NW + 2;
     m.zb = p;  p += D::NW;
     m.items = reinterpret_cast<unsigned short*>(p);
+    m.half_ofs = 2 * a.max_faces;
     seg_ofs = sfo0 + 40 * SAB_COPIES + warp * 32;
   }
   __syncthreads();
@@ -970,14 +992,13 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
     else                                           // overrun the staging area, report the problem "not solved"
     {
       const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
-      double2* dst = reinterpret_cast<double2*>(sAb);
       int bad = 0;
       for (int i = lane; i < 2 * nf; i += 32)
       {
         double2 v = src[i];
         bad |= !(fabs(v.x) < 1e300) || !(fabs(v.y) < 1e300);
         if (i & 1) v.y += a.row_tol;               // rows are staged as [Ax Ay Az b+tol]
-        dst[i] = v;
+        row_store(sAb, i, m.half_ofs, v);
       }
       for (int i = lane; i <= P && i < 36; i += 32) sfo[i] = a.face_ofs[p0 + i] - f0;
       rows_bad = __any_sync(FULL, bad) != 0 ? 1 : 0;
@@ -1031,14 +1052,13 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
     {
       const bool fits = nf >= 0 && nf <= a.max_faces;      // see the warp-adopting variant above
       const double2* src = reinterpret_cast<const double2*>(a.Ab + (size_t)4 * f0);
-      double2* dst = reinterpret_cast<double2*>(sAb);
       int bad = 0;
       for (int i = threadIdx.x; fits && i < 2 * nf; i += blockDim.x)
       {
         double2 v = src[i];
         bad |= !(fabs(v.x) < 1e300) || !(fabs(v.y) < 1e300);
         if (i & 1) v.y += a.row_tol;               // rows are staged as [Ax Ay Az b+tol]
-        dst[i] = v;
+        row_store(sAb, i, m.half_ofs, v);
       }
       for (int i = threadIdx.x; i <= P && i < 36; i += blockDim.x) sfo[i] = a.face_ofs[p0 + i] - f0;
       rows_bad = __syncthreads_or(bad) != 0 ? 1 : 0;       // also the barrier that publishes the staged rows

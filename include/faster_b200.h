@@ -77,6 +77,18 @@ int fq_solve_batch(fq_ctx* ctx, int N, int force_final, const double* x0, const 
                    int P, const int* face_ofs, const double* Ab, int n_cand, const double* dt,
                    const uint8_t* sigma, uint8_t* feasible, double* cost, double* coeffs, int32_t* iters);
 
+/* fq_solve_batch, plus a PROOF for every candidate reported infeasible: the Farkas certificate the solver stopped on, so
+ * that a caller (tests/test_certificates_gpu.py) can verify the flag on the literal rows of the reference's model without
+ * trusting the solver.  cert[i*cert_stride ..]: [0] n = number of rows, [1] violation of the entering row at the last
+ * iterate, then n pairs (row id, multiplier >= 0); the pairs' rows are inconsistent: sum mult_k row_k = 0 in the free
+ * directions and sum mult_k rhs_k < 0.  Row ids: box rows (solverGurobi.cpp:390-407) 1000000 + type*10000 + axis*1000 +
+ * t*10 + s with type 0/1/2 = v/a/j at the start of segment t, s = 1 for "<= +max", 0 for ">= -max"; corridor rows
+ * (:249-287) t*100000 + f*10 + k: face f (row of Ab) on control point k of segment t.  n = 0: feasible, or abandoned.
+ * cert_stride >= 4 + 6 FQ_MAX_N.  Runs the size-generic kernel (which tracks row identities); HOST pointers. */
+int fq_solve_batch_cert(fq_ctx* ctx, int N, int force_final, const double* x0, const double* xf, const double* lim,
+                        int P, const int* face_ofs, const double* Ab, int n_cand, const double* dt,
+                        const uint8_t* sigma, uint8_t* feasible, double* cost, double* cert, int cert_stride);
+
 /* n_prob corridor problems in one launch; HOST pointers.  Problem j owns candidates
  * cand_ofs[j] .. cand_ofs[j+1]-1 and polytopes poly_ofs[j] .. poly_ofs[j+1]-1 (indices into face_ofs, which has
  * poly_ofs[n_prob]+1 entries).  x0/xf are n_prob*9, lim n_prob*3.  Outputs as fq_solve_batch. */

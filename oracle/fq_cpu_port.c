@@ -175,6 +175,11 @@ typedef struct { uint64_t dt_bits, sigpack; uint32_t mask; } memo_entry;
 typedef struct { atomic_int n[MEMO_NB], ready[MEMO_NB][MEMO_BE]; memo_entry e[MEMO_NB][MEMO_BE]; } memo_t;
 static inline int memo_bucket(uint64_t dt_bits) { return (int)((dt_bits * 0x9E3779B97F4A7C15ull) >> 40) % MEMO_NB; }
 static int g_memo_on = 1;
+static int g_memo_lookup = 1;      /* analysis: 0 = record certificates but never answer from the memo */
+void fqc_set_memo_lookup(int on) { g_memo_lookup = on; }
+static int32_t* g_cert_out = NULL;   /* analysis only: per candidate, the certificate's segment mask (-1: none) */
+void fqc_set_cert_out(int32_t* p) { g_cert_out = p; }
+static __thread long g_cur_cand = -1;
 void fqc_set_memo(int on) { g_memo_on = on; }
 static atomic_long g_memo_hits, g_memo_inserts;
 void fqc_memo_stats(long* hits, long* inserts, int reset)
@@ -206,7 +211,7 @@ static int solve_one(const plan_t* p, work_t* k, const double* x0, const double*
     for (int t = 0; t < N; t++) sigpack |= (uint64_t)(sigma[t] < P ? sigma[t] : P - 1) << (4 * t);
     const int bk = memo_bucket(dt_bits);
     const int n = atomic_load_explicit(&memo->n[bk], memory_order_acquire);
-    for (int i = 0; i < n && i < MEMO_BE; i++)
+    for (int i = 0; g_memo_lookup && i < n && i < MEMO_BE; i++)
       if (atomic_load_explicit(&memo->ready[bk][i], memory_order_acquire) && memo->e[bk][i].dt_bits == dt_bits &&
           ((memo->e[bk][i].sigpack ^ sigpack) & nibble_mask(memo->e[bk][i].mask)) == 0)
       {
@@ -342,6 +347,7 @@ static int solve_one(const plan_t* p, work_t* k, const double* x0, const double*
           uint32_t mask = bseg ? 1u << (bseg - 1) : 0u;
           for (int c = 0; c < q; c++)
             if (k->r[c] < 0) { sr -= k->r[c]; if (k->aseg[c]) mask |= 1u << (k->aseg[c] - 1); }
+          if (g_cert_out && g_cur_cand >= 0) g_cert_out[g_cur_cand] = viol > MEMO_MARGIN * (1.0 + sr) ? (int32_t)mask : -1;
           if (viol > MEMO_MARGIN * (1.0 + sr))
           {
             const int bk = memo_bucket(dt_bits);
@@ -460,6 +466,7 @@ static void run_job(const job_t* jb, work_t* wk)
       for (int i = 0; i <= P && i < 64; i++) fo[i] = jb->face_ofs[p0 + i] - f0;
       double cst = INFINITY;
       int it = 0;
+      g_cur_cand = c;
       const int st = solve_one(jb->plan, wk, jb->x0 + 9 * prob, jb->xf + 9 * prob, jb->lim + 3 * prob, jb->dt[c], P, fo, jb->Ab + 4 * (size_t)f0,
                                jb->sigma ? jb->sigma + (size_t)c * N : NULL, &cst, jb->coeffs ? jb->coeffs + (size_t)c * 12 * N : NULL, &it,
                                jb->memo && jb->sigma ? jb->memo + prob : NULL);

@@ -1,0 +1,110 @@
+"""Parity evidence that does NOT go through oracle/fq_oracle.c:
+  (1) the CUDA path against HiGHS on the LITERAL model of the reference (oracle/model_fullspace.py: the reference's own
+      12N coefficient variables, every row as solverGurobi.cpp writes it), on samples of BASELINE configs 2, 3 and 5;
+  (2) for candidates the GPU reports infeasible, the Farkas certificate the solver stopped on (fq_solve_batch_cert) is
+      checked on those literal rows: multipliers y >= 0 on the inequality rows, free multipliers on the equality rows
+      (initial state, final state, continuity), combination of the rows = 0, combination of the right-hand sides < 0.
+      Such a certificate proves infeasibility whatever solver produced it.
+"""
+import numpy as np
+import pytest
+
+from faster_b200 import corridor as cr
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("cfg2", 10, 3, True, "uav"), ("cfg3", 10, 4, False, "uav"), ("cfg5", 15, 8, True, "ground")]
+
+
+def _candidates(N, P, ff, profile, seed, n_sig, rng):
+    pb = cr.make_corridor(seed, P, N, profile, ff)
+    allm = cr.monotone_sigmas(N, P) if P <= 4 else cr.sample_monotone_sigmas(N, P, 400, rng)
+    sig = allm[rng.choice(len(allm), n_sig, replace=False)]
+    from faster_b200 import capi
+    base = max(capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N), 0.02)
+    fac = np.array([1.0, 2.0, 3.0, 5.0, 8.0])
+    dts = np.repeat(fac * base, n_sig)
+    sigs = np.tile(sig, (len(fac), 1))
+    return pb, dts, sigs
+
+
+@pytest.mark.parametrize("name,N,P,ff,profile", CASES)
+def test_cuda_path_against_highs_on_the_literal_model(solver, name, N, P, ff, profile):
+    from oracle import model_fullspace as mf
+    rng = np.random.default_rng(sum(map(ord, name)))
+    checked = feas_seen = infeas_seen = 0
+    for seed in (6100, 6101, 6102):
+        pb, dts, sigs = _candidates(N, P, ff, profile, seed, 6, rng)
+        fg, cg, cog, _ = solver.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff, want_coeffs=True)
+        for i in range(len(dts)):
+            ok, cost, z = mf.solve_highs(N, pb["x0"], pb["xf"], pb["lim"], dts[i], pb["polys"], sigs[i], ff)
+            assert bool(fg[i]) == bool(ok), (name, seed, i, dts[i], sigs[i])
+            checked += 1
+            if ok:
+                feas_seen += 1
+                assert abs(cg[i] - cost) <= 1e-5 * max(1.0, abs(cost)), (cg[i], cost)
+                assert np.abs(cog[i] - z).max() <= 1e-3 * max(1.0, np.abs(z).max())       # HiGHS' own accuracy on the coefficients
+            else:
+                infeas_seen += 1
+    assert checked == 90 and feas_seen > 10 and infeas_seen > 5
+
+
+def _literal_row_index(N, polys, sigma):
+    """Row numbers of oracle/model_fullspace.build's inequality block for the certificate's row ids."""
+    face_ofs = np.concatenate([[0], np.cumsum([len(b) for _, b in polys])]).astype(int)
+    box = {}
+    r = 0
+    for t in range(N):
+        for ax in range(3):
+            for typ in range(3):
+                box[(typ, ax, t, 1)] = r
+                box[(typ, ax, t, 0)] = r + 1
+                r += 2
+    cor = {}
+    for t in range(N):
+        p = int(sigma[t])
+        F = len(polys[p][1])
+        for k in range(4):
+            for f in range(F):
+                cor[(t, face_ofs[p] + f, k)] = r
+                r += 1
+    return box, cor, r
+
+
+@pytest.mark.parametrize("name,N,P,ff,profile", CASES)
+def test_infeasibility_certificates_hold_on_the_literal_rows(solver, name, N, P, ff, profile):
+    from oracle import model_fullspace as mf
+    rng = np.random.default_rng(7 + N + P)
+    verified = 0
+    for seed in (6200, 6201, 6202, 6203):
+        pb, dts, sigs = _candidates(N, P, ff, profile, seed, 8, rng)
+        fg, _, cert = solver.solve_batch_cert(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff)
+        f2, _, _, _ = solver.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff)
+        assert np.array_equal(fg, f2)                          # generic (certifying) and specialised kernel agree
+        for i in np.flatnonzero(fg == 0)[:12]:
+            n = int(cert[i, 0])
+            assert n >= 1, "infeasible candidate without certificate"
+            Q, Aeq, beq, Ain, bin_ = mf.build(N, pb["x0"], pb["xf"], pb["lim"], dts[i], pb["polys"], sigs[i], ff)
+            box, cor, n_rows = _literal_row_index(N, pb["polys"], sigs[i])
+            assert n_rows == len(bin_)
+            y = np.zeros(len(bin_))
+            for k in range(n):
+                rid, mult = int(round(cert[i, 2 + 2 * k])), cert[i, 3 + 2 * k]
+                assert mult >= -1e-12
+                if rid >= 1000000:
+                    rid -= 1000000
+                    typ, rem = divmod(rid, 10000); ax, rem = divmod(rem, 1000); t, s = divmod(rem, 10)
+                    y[box[(typ, ax, t, s)]] += mult
+                else:
+                    t, rem = divmod(rid, 100000); f, kcp = divmod(rem, 10)
+                    y[cor[(t, f, kcp)]] += mult
+            g = Ain.T @ y                                      # must vanish modulo the equality rows
+            mu, *_ = np.linalg.lstsq(Aeq.T, -g, rcond=None)
+            resid = np.abs(g + Aeq.T @ mu).max()
+            scale = max(1.0, np.abs(g).max())
+            assert resid <= 1e-7 * scale, (name, seed, i, resid, scale)
+            gap = float(bin_ @ y + beq @ mu)                   # < 0: the rows cannot hold together
+            assert gap < -1e-9, (name, seed, i, gap)
+            assert abs(gap + cert[i, 1]) <= 1e-6 * max(1.0, abs(gap)), (gap, cert[i, 1])   # = minus the violation the solver saw
+            verified += 1
+    assert verified >= 10
