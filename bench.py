@@ -469,6 +469,34 @@ def main():
     # ---- parity: a slice of batch 0 against the CPU restatement of the chain, and the tolerance / margin picture
     if rank == 0 and not args.no_cpu_baseline:
         line["parity"] = parity_block(batches[0], res0, e2e_solvers[0], torch, capi, dev)
+    # ---- what a planner needs from a replan is the WINNERS (first feasible factor, then minimum cost): with the library's
+    #      early exit (option "sweep_early_exit") candidates that cannot win are not evaluated.  Not the BASELINE metric
+    #      (those candidates are not solved); reported as replans (corridor pairs) per second beside the full evaluation.
+    if rank == 0:
+        ee = capi.Solver(local)
+        ee.set_option("sweep_early_exit", 1)
+        rates = {}
+        for name, sv in (("full_evaluation", e2e_solvers[0]), ("early_exit", ee)):
+            for _ in range(3):
+                sv.replan_pairs_dev(batches[0].args, 0, tstream.cuda_stream)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(tstream)
+            for p in range(inner):
+                sv.replan_pairs_dev(batches[p % ring].args, 0, tstream.cuda_stream)
+            a1.record(tstream)
+            torch.cuda.synchronize()
+            rates[name] = C * inner / (a0.elapsed_time(a1) * 1e-3)
+            if name == "early_exit":
+                res_ee = batches[(inner - 1) % ring].results(capi)
+        sv = e2e_solvers[0]
+        sv.replan_pairs_dev(batches[(inner - 1) % ring].args, 0, tstream.cuda_stream)
+        torch.cuda.synchronize()
+        res_full = batches[(inner - 1) % ring].results(capi)
+        line["replans_per_s"] = {"full_evaluation": rates["full_evaluation"], "early_exit": rates["early_exit"], "unit": "corridor pairs/s",
+                                 "how": "fq_replan_pairs_dev, one context / stream, %d corridors per pass" % C,
+                                 "same_winners": bool(res_ee.tobytes() == res_full.tobytes())}
+        ee.close()
     # ---- single-replan latency (what the robot experiences against its 10 ms budget)
     if rank == 0:
         line["replan_latency_us"] = latency_block(e2e_solvers[0], capi)

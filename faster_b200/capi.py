@@ -14,7 +14,7 @@ EXPORTS = ["fq_abi_version", "fq_create", "fq_destroy", "fq_last_error", "fq_set
            "fq_solve_multi_async", "fq_wait", "fq_solve_multi_dev", "fq_gen_new_traj", "fq_gen_new_traj_sampled", "fq_gen_new_traj_exact", "fq_dt_initial", "fq_num_samples", "fq_fill_x",
            "fq_monotone_sigmas", "fq_plan_tables", "fq_ellipsoid_decomp", "fq_jps3d_plan", "fq_jps3d_plan_world", "fq_jps3d_rules",
            "fq_replan_pairs", "fq_replan_pairs_async", "fq_replan_pairs_dev", "fq_create_multi", "fq_comm_unique_id", "fq_comm_init",
-           "fq_comm_info", "fq_allgather_dev", "fq_shard_range", "fq_solve_multi_sharded", "fq_solve_batch_cert"]
+           "fq_comm_info", "fq_allgather_dev", "fq_shard_range", "fq_solve_multi_sharded", "fq_solve_batch_cert", "fq_has_feature"]
 
 
 class FqError(RuntimeError):
@@ -222,6 +222,12 @@ def plan_tables(N, force_final):
     if r == 0:
         raise FqError("unsupported (N, force_final)")
     return TZ, T0, FT
+
+
+def has_feature(name):
+    L = lib()
+    L.fq_has_feature.argtypes = [C.c_char_p]
+    return bool(L.fq_has_feature(name.encode()))
 
 
 def shard_range(n_prob, cand_ofs, rank, world):

@@ -104,6 +104,7 @@ extern "C" void fq_destroy(fq_ctx* ctx)
   ctx->h_in.release(); ctx->h_out.release();
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_memo) cudaFree(ctx->d_memo);
+  if (ctx->d_first) cudaFree(ctx->d_first);
   if (ctx->ev_head) cudaEventDestroy(ctx->ev_head);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -117,6 +118,7 @@ extern "C" int fq_set_option(fq_ctx* ctx, const char* key, int value)
   if (std::string(key) == "throughput_slices") { ctx->throughput_slices = value > 0 && value <= 64 ? value : 0; return 0; }
   if (std::string(key) == "max_faces_per_polytope") { ctx->max_poly_faces_hint = value > 0 ? value : 0; return 0; }
   if (std::string(key) == "cert_memo") { ctx->cert_memo = value != 0; return 0; }
+  if (std::string(key) == "sweep_early_exit") { ctx->early_exit = value != 0; return 0; }
   if (std::string(key) == "row_tol_1e9")
   { // row tolerance in units of 1e-9 (10 = the default 1e-8, 1000 = Gurobi's default FeasibilityTol 1e-6); >= 0
     if (value < 0 || value > 1000000) return fail(ctx, FQ_E_ARG, "row_tol_1e9 out of range (0..1000000)");
@@ -124,6 +126,15 @@ extern "C" int fq_set_option(fq_ctx* ctx, const char* key, int value)
     return 0;
   }
   return fail(ctx, FQ_E_ARG, std::string("unknown option ") + key);
+}
+
+extern "C" int fq_has_feature(const char* name)
+{
+  if (!name) return 0;
+  const std::string n(name);
+  if (n == "cert_memo") return FQ_CERT_MEMO ? 1 : 0;
+  if (n == "sweep_early_exit" || n == "replan_pairs" || n == "multi_gpu" || n == "row_tol" || n == "certificates") return 1;
+  return 0;
 }
 
 extern "C" const char* fq_last_error(const fq_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -152,12 +163,21 @@ int fq_launch_solve_ctx(fq_ctx* ctx, int N, int force_final, int n_prob, const d
     FQ_CUDA(cudaDeviceSynchronize());
     cudaFree(ctx->d_counters);
     ctx->d_counters = nullptr;
+    if (ctx->d_first) { cudaFree(ctx->d_first); ctx->d_first = nullptr; }
     ctx->counters_cap = n_prob + n_prob / 2;
     FQ_CUDA(cudaMalloc(&ctx->d_counters, sizeof(int) * (size_t)kCounterSlots * ctx->counters_cap));
   }
   const unsigned slot = ctx->counters_pos++ % kCounterSlots;
   int* counters = ctx->d_counters + (size_t)slot * ctx->counters_cap;
   a.memo = nullptr; a.memo_salt = 0; a.cert = ctx->cert_out; a.cert_stride = ctx->cert_stride;
+  a.first_feasible = nullptr; a.sorted_dt = ctx->launch_sorted_dt ? 1 : 0;
+  ctx->launch_sorted_dt = false;
+  if (ctx->early_exit && max_cand > 1)
+  {
+    if (!ctx->d_first) FQ_CUDA(cudaMalloc(&ctx->d_first, sizeof(unsigned long long) * (size_t)kCounterSlots * ctx->counters_cap));
+    a.first_feasible = ctx->d_first + (size_t)slot * ctx->counters_cap;
+    FQ_CUDA(cudaMemsetAsync(a.first_feasible, 0xff, sizeof(unsigned long long) * (size_t)n_prob, stream));
+  }
 #if FQ_CERT_MEMO
   if (ctx->cert_memo && n_prob <= kFqMemoProbs && max_cand >= 32)
   { // infeasibility certificates shared between the candidates of a problem (fq_kernels_t.cuh); entries of earlier
@@ -845,7 +865,7 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
     L.k.poly_ofs = (const int*)(db + opo); L.k.face_ofs = (const int*)(db + ofo); L.k.Ab = (const double*)(db + oAb);
     L.k.max_faces = n_face; L.k.item_cap = N * max_pf; L.k.cand_ofs = nullptr; L.k.dt = nullptr; L.k.sigma = nullptr;
     L.k.feasible = nullptr; L.k.cost = nullptr; L.k.coeffs = nullptr; L.k.iters = nullptr; L.k.row_tol = ctx->row_tol;
-    L.k.memo = nullptr; L.k.memo_salt = 0; L.k.cert = nullptr; L.k.cert_stride = 0;
+    L.k.memo = nullptr; L.k.memo_salt = 0; L.k.cert = nullptr; L.k.cert_stride = 0; L.k.first_feasible = nullptr; L.k.sorted_dt = 0;
     L.n_dt = n_dt; L.P = P; L.dts = (const double*)(db + odts); L.roots = (const int*)(db + oroot);
     L.incumbent = (unsigned long long*)(db + oinc); L.leaves = db + oleaf; L.n_leaves = (int*)(db + ocnt) + 1;
     L.leaf_cap = leaf_cap; L.flags = (int*)(db + ocnt) + 2; L.n_children = (int*)(db + ocnt); L.cap = cap;

@@ -72,6 +72,9 @@ struct fq_ctx
   FqMemoEntry* d_memo = nullptr;  // ring of infeasibility-certificate memos: one slot per launch in flight (as d_counters)
   unsigned memo_salt = 0;         // launch counter stamped into the memo entries (stale entries carry another value)
   bool cert_memo = true;          // option "cert_memo"
+  bool early_exit = false;        // option "sweep_early_exit": candidates that cannot win genNewTraj's selection are skipped
+  bool launch_sorted_dt = false;  // set by the chained replan for its next launch: candidate lists are in ascending dt order
+  unsigned long long* d_first = nullptr;   // ring (as d_counters) of per-problem "smallest feasible dt so far"
   double* cert_out = nullptr;     // fq_solve_batch_cert: device buffer the generic kernel writes certificates into
   int cert_stride = 0;
   // ---- multi-GPU (fq_multi.cu)

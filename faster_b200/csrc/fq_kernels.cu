@@ -187,7 +187,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
     // ================= most violated row =================
     double bv = a.row_tol, bw0 = 0, bw1 = 0, bw2 = 0, bh = 0;
     int by = 0, bid = 0;   // bid: row identity for the certificate export (fq_solve_batch_cert): box rows
-                           // 1000000 + type*10000 + axis*1000 + t*10 + (upper bound ? 1 : 0); corridor rows t*100000 + face*10 + cp
+                           // 10000000 + type*10000 + axis*1000 + t*10 + (upper bound ? 1 : 0); corridor rows t*100000 + face*10 + cp
     for (int i = lane; i < 9 * N; i += 32)
     { // |v|,|a|,|j| boxes at segment starts (solverGurobi.cpp:390-407); type 0 v, 1 a, 2 j
       const int type = i / (3 * N), rem = i - type * 3 * N, ax = rem / N, t = rem - ax * N;
@@ -200,7 +200,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
       {
         const double s = val > 0 ? sinv : -sinv;
         bv = viol; by = y; bh = L;
-        bid = 1000000 + type * 10000 + ax * 1000 + t * 10 + (val > 0 ? 1 : 0);
+        bid = 10000000 + type * 10000 + ax * 1000 + t * 10 + (val > 0 ? 1 : 0);
         bw0 = ax == 0 ? s : 0.0; bw1 = ax == 1 ? s : 0.0; bw2 = ax == 2 ? s : 0.0;
       }
     }

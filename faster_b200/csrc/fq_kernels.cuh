@@ -61,6 +61,10 @@ struct FqKernelArgs
   // infeasibility-certificate memo of this launch (fq_kernels_t.cuh), or nullptr: n_prob x FQ_MEMO_NB x FQ_MEMO_BE entries
   struct FqMemoEntry* memo;
   unsigned memo_salt;    // unique per launch of a context: entries carrying another salt are stale
+  // "first feasible dt wins" early exit (option "sweep_early_exit"; specialised kernel only): per problem the smallest dt
+  // (bit pattern) of a candidate found feasible so far, or nullptr.  Candidates with a larger dt are not evaluated.
+  unsigned long long* first_feasible;
+  int sorted_dt;         // candidates of every problem are in ascending dt order (the chained replan's grids)
   // size-generic kernel only (fq_solve_batch_cert): per infeasible candidate, [n, violation, (row id, multiplier) x n]
   double* cert;
   int cert_stride;
@@ -76,7 +80,13 @@ struct FqMemoEntry
 #define FQ_MEMO_NB 16         // buckets per problem (hash of dt)
 #define FQ_MEMO_BE 16         // entries per bucket: one per lane of a half warp
 #ifndef FQ_CERT_MEMO
-#define FQ_CERT_MEMO 1        // 0 compiles the memo out (A/B runs)
+#define FQ_CERT_MEMO 0        // 1 compiles the memo in.  MEASURED NEGATIVE on the bench workload (same box, tools/ab.sh, cfg4
+                              // chain): compiled out 72.4 M pairs/s; compiled in but switched off 64.2 M (the bookkeeping of
+                              // the active rows' segments costs 11 %); switched on 57.3 M.  With ~2400 warps working on 64
+                              // corridors at once and only ~28 candidates per warp per launch, few candidates start after a
+                              // useful proof exists (a scheduling model of the launch gives 9 % hits and 3 % at best), and the
+                              // commonest proofs (a constant control point of segment 0 outside its polytope) already cost a
+                              // single iteration.  It pays on the CPU port (8-128 threads: 142 -> 66 ms per pass), where it is on.
 #endif
 #define FQ_MEMO_MARGIN 1e-5   // certificates are recorded only when the violation exceeds this x (1 + sum |multipliers|)
 

@@ -886,6 +886,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
     a.feasible[cand] = status == 1;
     a.cost[cand] = status == 1 ? cost : INFINITY;
     if (a.iters) a.iters[cand] = status == -1 ? -it : it;
+    if (status == 1 && a.first_feasible) atomicMin(a.first_feasible + prob, (unsigned long long)__double_as_longlong(dt));
   }
   if (a.coeffs)
   {
@@ -1007,11 +1008,43 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
     int c = 0;
     if (lane == 0) c = atomicAdd(counters + prob, 1);
     c = __shfl_sync(FULL, c, 0);
+    const bool ee = a.first_feasible != nullptr;   // early exit: genNewTraj's "first feasible factor wins" (solverGurobi.cpp:445-446)
     while (c < count)
     {
       int cn = 0;
       if (lane == 0) cn = atomicAdd(counters + prob, 1);
-      solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, c_begin + (count - 1 - c), lane, rows_bad);
+      // claims run from the end of the list (long solves first); with the early exit from its start (smallest dt first)
+      const int cand = c_begin + (ee ? c : count - 1 - c);
+      bool skip = false;
+      if (ee)
+      {
+        const unsigned long long best = *reinterpret_cast<volatile unsigned long long*>(a.first_feasible + prob);
+        skip = (unsigned long long)__double_as_longlong(a.dt[cand]) > best;   // a smaller dt already has a feasible candidate
+      }
+      if (!skip) solve_candidate<D>(a, TZ, SY, sAb, sfo, m, seg_ofs, prob, cand, lane, rows_bad);
+      else
+      { // not evaluated: it cannot win.  Reported like an unsolved candidate, iters = -3 marks the reason.
+        if (a.sorted_dt)
+        { // ascending dt: every candidate after this one is beaten too -- take them all at once
+          int old = 0;
+          if (lane == 0) old = atomicExch(counters + prob, count + 1);
+          old = __shfl_sync(FULL, old, 0);
+          if (old < count)
+            for (int i = c_begin + old + lane; i < c_begin + count; i += 32)
+            {
+              a.feasible[i] = 0; a.cost[i] = INFINITY;
+              if (a.iters) a.iters[i] = -3;
+              if (a.coeffs) for (int k = 0; k < 12 * D::N; k++) a.coeffs[(size_t)i * D::N * 12 + k] = 0.0;
+            }
+        }
+        if (lane == 0)
+        {
+          a.feasible[cand] = 0; a.cost[cand] = INFINITY;
+          if (a.iters) a.iters[cand] = -3;
+        }
+        if (a.coeffs)
+          for (int idx = lane; idx < 12 * D::N; idx += 32) a.coeffs[(size_t)cand * D::N * 12 + idx] = 0.0;
+      }
       c = __shfl_sync(FULL, cn, 0);
     }
     __syncwarp();

@@ -94,6 +94,7 @@ extern "C" int fq_replan_pairs_dev(fq_ctx* ctx, const fq_pair_args* a, fq_pair_r
     FQ_CUDA(fq_launch_dtbase(P, Nw, a->DC, a->x0, a->xf_whole, a->lim, s.dt_base_w, st));
     FQ_CUDA(fq_launch_expand_grid(P, Nw, a->n_fac_whole, a->n_sig_whole, a->factors_whole, a->sigmas_whole, s.dt_base_w, s.dt_w,
                                   s.sig_w, s.cand_ofs_w, st));
+    ctx->launch_sorted_dt = true;              // the grid is factor-major with ascending factors
     int rc = fq_launch_solve_ctx(ctx, Nw, 1, P, a->x0, a->xf_whole, a->lim, a->poly_ofs_whole, a->face_ofs_whole, a->Ab_whole,
                                  s.cand_ofs_w, mcw, a->max_faces_whole, a->max_poly_faces_whole, s.dt_w, s.sig_w, feas_w, cost_w,
                                  nullptr, nullptr, st);
@@ -116,6 +117,7 @@ extern "C" int fq_replan_pairs_dev(fq_ctx* ctx, const fq_pair_args* a, fq_pair_r
     FQ_CUDA(fq_launch_dtbase(P, Ns, a->DC, s.x0_safe, a->xf_safe, a->lim, s.dt_base_s, st));
     FQ_CUDA(fq_launch_expand_grid(P, Ns, a->n_fac_safe, a->n_sig_safe, a->factors_safe, a->sigmas_safe, s.dt_base_s, s.dt_s,
                                   s.sig_s, s.cand_ofs_s, st));
+    ctx->launch_sorted_dt = true;
     rc = fq_launch_solve_ctx(ctx, Ns, 0, P, s.x0_safe, a->xf_safe, a->lim, a->poly_ofs_safe, a->face_ofs_safe, a->Ab_safe,
                              s.cand_ofs_s, mcs, a->max_faces_safe, a->max_poly_faces_safe, s.dt_s, s.sig_s, feas_s, cost_s, nullptr,
                              nullptr, st);
@@ -187,6 +189,10 @@ int fq_replan_pairs_host_ex(fq_ctx* ctx, const fq_pair_args* a, bool deferred, f
   if (!fq_scan_all_positive_finite(a->lim, 3 * (size_t)P) || !fq_scan_all_positive_finite(a->factors_whole, (size_t)a->n_fac_whole) ||
       !fq_scan_all_positive_finite(a->factors_safe, (size_t)a->n_fac_safe))
     return fq_fail(ctx, FQ_E_ARG, "limits and factors must be finite and > 0");
+  for (int i = 1; i < a->n_fac_whole; i++)
+    if (a->factors_whole[i] < a->factors_whole[i - 1]) return fq_fail(ctx, FQ_E_ARG, "factors_whole must be ascending");
+  for (int i = 1; i < a->n_fac_safe; i++)
+    if (a->factors_safe[i] < a->factors_safe[i - 1]) return fq_fail(ctx, FQ_E_ARG, "factors_safe must be ascending");
   if (n_poly_w > 0 && !a->sigmas_whole) return fq_fail(ctx, FQ_E_ARG, "sigmas_whole is NULL");
   if (n_poly_s > 0 && !a->sigmas_safe) return fq_fail(ctx, FQ_E_ARG, "sigmas_safe is NULL");
   // assignments must name existing polytopes of EVERY corridor they are applied to

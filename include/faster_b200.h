@@ -40,6 +40,9 @@ extern "C" {
 typedef struct fq_ctx fq_ctx;     /* opaque: device, stream, plan tables, scratch             */
 
 int fq_abi_version(void);
+/* 1 if this build has the named feature: "cert_memo" (compile-time switch FQ_CERT_MEMO, off by default: see
+ * faster_b200/csrc/fq_kernels.cuh), "sweep_early_exit", "replan_pairs", "multi_gpu", "row_tol", "certificates". */
+int fq_has_feature(const char* name);
 
 /* Threading: a context is used from one thread at a time, like a SolverGurobi instance in the reference (one replan
  * callback); different contexts are independent.  With fq_solve_multi_dev at most 64 launches of one
@@ -56,9 +59,13 @@ const char* fq_last_error(const fq_ctx* ctx);   /* ctx may be NULL: last creatio
  * default: 4, or 2 for fq_solve_multi_async): how many launches a large host batch is cut into (upload / solve / download of consecutive slices
  * overlap on two streams).  "max_faces_per_polytope": see fq_solve_multi_dev.  "row_tol_1e9" (0..1000000): the absolute row
  * tolerance of every later solve of the context in units of 1e-9 -- 10 is the default FQ_ROW_TOL = 1e-8, 1000 is Gurobi's
- * default FeasibilityTol 1e-6 (the reference sets no tolerance parameter, solverGurobi.cpp:479-487).  "cert_memo" (0/1, default 1):
- * candidates of one problem share their infeasibility proofs (a candidate whose dt and polytopes on the proof's segments
+ * default FeasibilityTol 1e-6 (the reference sets no tolerance parameter, solverGurobi.cpp:479-487).  "cert_memo" (0/1; only in builds with
+ * fq_has_feature("cert_memo")): candidates of one problem share their infeasibility proofs (a candidate whose dt and polytopes on the proof's segments
  * match a recorded Farkas certificate is answered without a solve; same flags, iters = 0 marks them).
+ * "sweep_early_exit" (0/1, default 0): genNewTraj keeps the FIRST feasible factor (solverGurobi.cpp:445-446), so once a
+ * problem has a feasible candidate, candidates with a larger dt cannot win; with this option they are not evaluated
+ * (reported feasible = 0, cost = +inf, iters = -3) and claims run in ascending dt.  The winners (fq_replan_pairs results,
+ * fq_gen_new_traj*, fq_solve_multi_sharded's winners) are unchanged; the per-candidate arrays are no longer complete.
  * Returns 0 or FQ_E_ARG. */
 int fq_set_option(fq_ctx* ctx, const char* key, int value);
 
@@ -81,7 +88,7 @@ int fq_solve_batch(fq_ctx* ctx, int N, int force_final, const double* x0, const 
  * that a caller (tests/test_certificates_gpu.py) can verify the flag on the literal rows of the reference's model without
  * trusting the solver.  cert[i*cert_stride ..]: [0] n = number of rows, [1] violation of the entering row at the last
  * iterate, then n pairs (row id, multiplier >= 0); the pairs' rows are inconsistent: sum mult_k row_k = 0 in the free
- * directions and sum mult_k rhs_k < 0.  Row ids: box rows (solverGurobi.cpp:390-407) 1000000 + type*10000 + axis*1000 +
+ * directions and sum mult_k rhs_k < 0.  Row ids: box rows (solverGurobi.cpp:390-407) 10000000 + type*10000 + axis*1000 +
  * t*10 + s with type 0/1/2 = v/a/j at the start of segment t, s = 1 for "<= +max", 0 for ">= -max"; corridor rows
  * (:249-287) t*100000 + f*10 + k: face f (row of Ab) on control point k of segment t.  n = 0: feasible, or abandoned.
  * cert_stride >= 4 + 6 FQ_MAX_N.  Runs the size-generic kernel (which tracks row identities); HOST pointers. */

@@ -112,8 +112,10 @@ def build(N, x0, xf, lim, dt, polys, sigma, force_final=True):
     return (Q, np.array(Aeq), np.array(beq), np.array(Ain), np.array(bin_))
 
 
-def solve_highs(N, x0, xf, lim, dt, polys, sigma, force_final=True):
-    """-> (feasible, cost, coeffs[N,12]).  cost = sum (6a)^2, i.e. Gurobi's ObjVal."""
+def solve_highs(N, x0, xf, lim, dt, polys, sigma, force_final=True, with_status=False):
+    """-> (feasible, cost, coeffs[N,12]).  cost = sum (6a)^2, i.e. Gurobi's ObjVal.  with_status=True appends HiGHS' model
+    status name ("kOptimal", "kInfeasible", or whatever it stopped with: its QP solver sometimes gives up on these
+    degenerate problems, which says nothing about feasibility)."""
     from scipy.optimize._highspy import _core as h
     Q, Aeq, beq, Ain, bin_ = build(N, x0, xf, lim, dt, polys, sigma, force_final)
     n = 12 * N
@@ -145,8 +147,9 @@ def solve_highs(N, x0, xf, lim, dt, polys, sigma, force_final=True):
     H.passModel(model)
     H.run()
     st = H.getModelStatus()
+    name = str(st).split(".")[-1]
     if st != h.HighsModelStatus.kOptimal:
-        return False, np.nan, None
+        return (False, np.nan, None, name) if with_status else (False, np.nan, None)
     z = np.array(H.getSolution().col_value)
     cost = float(np.sum((6.0 * z.reshape(N, 12)[:, :3]) ** 2))
-    return True, cost, z.reshape(N, 12)
+    return (True, cost, z.reshape(N, 12), name) if with_status else (True, cost, z.reshape(N, 12))

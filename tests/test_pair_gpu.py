@@ -235,3 +235,29 @@ def test_two_ranks_one_process_each(tmp_path):
     r1 = s.replan_pairs(w1, want_candidates=False, want_coeffs=False)["results"]
     s.close()
     assert a.tobytes() == r0.tobytes() + r1.tobytes()
+
+
+def test_early_exit_keeps_the_winners(solver):
+    """Option "sweep_early_exit": candidates that cannot win genNewTraj's selection (a smaller dt already has a feasible
+    candidate, solverGurobi.cpp:445-446) are not evaluated; the result records are bit-identical, the per-candidate flags
+    only lose feasible entries at larger dt."""
+    import bench
+    for w in (_synthetic_pairs(9, 7900, n_fac=8, n_sig=32), bench.load_cfg4(64, 16)):
+        full = solver.replan_pairs(w)
+        s2 = capi.Solver(0)
+        s2.set_option("sweep_early_exit", 1)
+        ee = s2.replan_pairs(w)
+        s2.close()
+        assert ee["results"].tobytes() == full["results"].tobytes()
+        assert np.array_equal(ee["coeffs_whole"], full["coeffs_whole"]) and np.array_equal(ee["coeffs_safe"], full["coeffs_safe"])
+        for k in ("whole", "safe"):
+            fe, ff = ee["feasible_" + k].astype(bool), full["feasible_" + k].astype(bool)
+            assert not (fe & ~ff).any()                               # nothing becomes feasible
+            assert fe.sum() < ff.sum()                                # and work was skipped
+            n, nf, ns = w["n_prob"], len(w["factors_" + k]), len(w["sigmas_" + k])
+            fe, ff = fe.reshape(n, nf, ns), ff.reshape(n, nf, ns)
+            for j in range(n):
+                d = ee["results"][k + "_dt_index"][j]
+                if d >= 0:                                            # everything up to the winning factor is complete
+                    assert np.array_equal(fe[j, :d + 1], ff[j, :d + 1])
+                    assert np.array_equal(ee["cost_" + k].reshape(n, nf, ns)[j, :d + 1], full["cost_" + k].reshape(n, nf, ns)[j, :d + 1])
