@@ -311,3 +311,35 @@ def make_forest_pair_safe(whole, R, N=10, P_safe=4):
     xf[:3] = path[-1]
     return dict(N=N, P=P_safe, x0=R[:9].copy(), xf=xf, lim=whole["lim"].copy(), polys=polys, force_final=False, DC=whole["DC"],
                 verts=path, seed=whole["seed"], profile="uav")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Feasibility margins ("hard parts"): Gurobi decides feasibility with FeasibilityTol 1e-6 on its own
+# scaled rows, this library with an absolute row tolerance (default 1e-8).  Candidates whose feasibility depends on
+# which of the two is used are FLAGGED (never dropped): a benchmark or a parity claim should say how many there are.
+# ------------------------------------------------------------------------------------------------------------------
+def margin_flags(solver, N, force_final, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dts, sigmas, eps=1e-5):
+    """For a fq_solve_multi workload: (feasible, near) with near[i] = True when candidate i's flag changes if every row
+    bound (polytope offsets b and the v/a/j limits) moves by -eps versus +eps, i.e. the candidate lies within eps (m,
+    m/s, m/s2, m/s3) of the feasibility boundary.  Three launches on `solver` (a faster_b200.capi.Solver)."""
+    f0 = solver.solve_multi(N, force_final, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dts, sigmas)[0]
+    out = []
+    for s in (-eps, eps):
+        A2 = np.ascontiguousarray(Ab).copy()
+        A2[:, 3] += s
+        out.append(solver.solve_multi(N, force_final, x0, xf, np.ascontiguousarray(lim + s), poly_ofs, face_ofs, A2, cand_ofs,
+                                      dts, sigmas)[0])
+    near = out[0] != out[1]
+    return f0, near
+
+
+def margin_report(solver, *args, eps_list=(1e-6, 1e-5, 1e-4)):
+    """{'within_<eps>': count} for several eps, plus the flags at the nominal tolerance."""
+    rep = {}
+    f0 = None
+    for e in eps_list:
+        f0, near = margin_flags(solver, *args, eps=e)
+        rep["within_%g" % e] = int(near.sum())
+    rep["candidates"] = int(len(f0))
+    rep["feasible"] = int(f0.sum())
+    return rep

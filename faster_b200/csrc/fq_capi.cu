@@ -170,8 +170,8 @@ int fq_launch_solve_ctx(fq_ctx* ctx, int N, int force_final, int n_prob, const d
   const unsigned slot = ctx->counters_pos++ % kCounterSlots;
   int* counters = ctx->d_counters + (size_t)slot * ctx->counters_cap;
   a.memo = nullptr; a.memo_salt = 0; a.cert = ctx->cert_out; a.cert_stride = ctx->cert_stride;
-  a.first_feasible = nullptr; a.sorted_dt = ctx->launch_sorted_dt ? 1 : 0;
-  ctx->launch_sorted_dt = false;
+  a.first_feasible = nullptr; a.sorted_dt = ctx->launch_sorted_dt ? 1 : 0; a.ee_width = ctx->launch_ee_width;
+  ctx->launch_sorted_dt = false; ctx->launch_ee_width = 0;
   if (ctx->early_exit && max_cand > 1)
   {
     if (!ctx->d_first) FQ_CUDA(cudaMalloc(&ctx->d_first, sizeof(unsigned long long) * (size_t)kCounterSlots * ctx->counters_cap));
@@ -660,6 +660,11 @@ int gen_new_traj_impl(fq_ctx* ctx, int N, int force_final, const double* x0, con
   char* din = (char*)ctx->d_in.p;
   char* dout = (char*)ctx->d_out.p;
   FQ_CUDA(cudaMemcpyAsync(din, hi, in_bytes, cudaMemcpyHostToDevice, st));
+  {
+    bool asc = true;
+    for (int d = 1; d < n_dt; d++) asc = asc && dts[d] >= dts[d - 1];
+    ctx->launch_sorted_dt = asc; ctx->launch_ee_width = asc ? n_sigma : 0;
+  }
   int rc = launch_solve(ctx, N, force_final, 1, (const double*)(din + ox0), (const double*)(din + oxf),
                         (const double*)(din + olim), (const int*)(din + opo), (const int*)(din + ofo),
                         (const double*)(din + oAb), (const int*)(din + oco), n_cand, n_face, max_pf,
@@ -865,7 +870,7 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
     L.k.poly_ofs = (const int*)(db + opo); L.k.face_ofs = (const int*)(db + ofo); L.k.Ab = (const double*)(db + oAb);
     L.k.max_faces = n_face; L.k.item_cap = N * max_pf; L.k.cand_ofs = nullptr; L.k.dt = nullptr; L.k.sigma = nullptr;
     L.k.feasible = nullptr; L.k.cost = nullptr; L.k.coeffs = nullptr; L.k.iters = nullptr; L.k.row_tol = ctx->row_tol;
-    L.k.memo = nullptr; L.k.memo_salt = 0; L.k.cert = nullptr; L.k.cert_stride = 0; L.k.first_feasible = nullptr; L.k.sorted_dt = 0;
+    L.k.memo = nullptr; L.k.memo_salt = 0; L.k.cert = nullptr; L.k.cert_stride = 0; L.k.first_feasible = nullptr; L.k.sorted_dt = 0; L.k.ee_width = 0;
     L.n_dt = n_dt; L.P = P; L.dts = (const double*)(db + odts); L.roots = (const int*)(db + oroot);
     L.incumbent = (unsigned long long*)(db + oinc); L.leaves = db + oleaf; L.n_leaves = (int*)(db + ocnt) + 1;
     L.leaf_cap = leaf_cap; L.flags = (int*)(db + ocnt) + 2; L.n_children = (int*)(db + ocnt); L.cap = cap;

@@ -74,6 +74,7 @@ struct fq_ctx
   bool cert_memo = true;          // option "cert_memo"
   bool early_exit = false;        // option "sweep_early_exit": candidates that cannot win genNewTraj's selection are skipped
   bool launch_sorted_dt = false;  // set by the chained replan for its next launch: candidate lists are in ascending dt order
+  int launch_ee_width = 0;        // ... and hold this many candidates per time allocation
   unsigned long long* d_first = nullptr;   // ring (as d_counters) of per-problem "smallest feasible dt so far"
   double* cert_out = nullptr;     // fq_solve_batch_cert: device buffer the generic kernel writes certificates into
   int cert_stride = 0;

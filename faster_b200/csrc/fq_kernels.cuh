@@ -65,6 +65,7 @@ struct FqKernelArgs
   // (bit pattern) of a candidate found feasible so far, or nullptr.  Candidates with a larger dt are not evaluated.
   unsigned long long* first_feasible;
   int sorted_dt;         // candidates of every problem are in ascending dt order (the chained replan's grids)
+  int ee_width;          // candidates per time allocation (0: unknown); sizes the grid of an early-exit sweep
   // size-generic kernel only (fq_solve_batch_cert): per infeasible candidate, [n, violation, (row id, multiplier) x n]
   double* cert;
   int cert_stride;

@@ -1132,15 +1132,38 @@ cudaError_t launch_t(const FqKernelArgs& a, long long total_cand_hint, cudaStrea
   const size_t smem = smem_bytes_t<N_, WHOLE_>(a.max_faces, a.item_cap);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;   // caller falls back to the size-generic kernel
   auto kern = fq_solve_kernel_t<N_, WHOLE_>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the shared-memory attribute and the occupancy query cost a few microseconds each: remembered per device (a replan
+  // calls this with the same sizes every 10 ms; the chained replan four times per batch)
+  struct Cached { size_t smem_set = 0, smem_occ = (size_t)-1; int per_sm = 0; };
+  static Cached cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
-  long long grid = (long long)per_sm * sm_count;
+  Cached local;
+  Cached& cc = (dev >= 0 && dev < 64) ? cache[dev] : local;
+  if (smem > cc.smem_set)
+  {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cc.smem_set = smem;
+  }
+  if (smem != cc.smem_occ)
+  {
+    int q = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, W * 32, smem);
+    if (e != cudaSuccess) return e;
+    cc.per_sm = q < 1 ? 1 : q;
+    cc.smem_occ = smem;
+  }
+  long long grid = (long long)cc.per_sm * sm_count;
   const long long need = (total_cand_hint + W - 1) / W;      // no point in more CTAs than candidates / warps
   if (grid > need) grid = need;
+  if (a.first_feasible && a.sorted_dt && a.ee_width > 0)
+  { // early exit on an ascending sweep: keep only ~two time allocations per problem in flight, so that the larger ones --
+    // which cannot win once a smaller one is feasible, and hold the long solves -- are mostly never started
+    const long long cap = ((long long)a.n_prob * 2 * a.ee_width + W - 1) / W;
+    if (grid > cap) grid = cap;
+  }
   if (grid < 1) grid = 1;
   e = cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)a.n_prob, stream);
   if (e != cudaSuccess) return e;

@@ -94,7 +94,7 @@ extern "C" int fq_replan_pairs_dev(fq_ctx* ctx, const fq_pair_args* a, fq_pair_r
     FQ_CUDA(fq_launch_dtbase(P, Nw, a->DC, a->x0, a->xf_whole, a->lim, s.dt_base_w, st));
     FQ_CUDA(fq_launch_expand_grid(P, Nw, a->n_fac_whole, a->n_sig_whole, a->factors_whole, a->sigmas_whole, s.dt_base_w, s.dt_w,
                                   s.sig_w, s.cand_ofs_w, st));
-    ctx->launch_sorted_dt = true;              // the grid is factor-major with ascending factors
+    ctx->launch_sorted_dt = true; ctx->launch_ee_width = a->n_sig_whole;   // factor-major grid, ascending factors
     int rc = fq_launch_solve_ctx(ctx, Nw, 1, P, a->x0, a->xf_whole, a->lim, a->poly_ofs_whole, a->face_ofs_whole, a->Ab_whole,
                                  s.cand_ofs_w, mcw, a->max_faces_whole, a->max_poly_faces_whole, s.dt_w, s.sig_w, feas_w, cost_w,
                                  nullptr, nullptr, st);
@@ -117,7 +117,7 @@ extern "C" int fq_replan_pairs_dev(fq_ctx* ctx, const fq_pair_args* a, fq_pair_r
     FQ_CUDA(fq_launch_dtbase(P, Ns, a->DC, s.x0_safe, a->xf_safe, a->lim, s.dt_base_s, st));
     FQ_CUDA(fq_launch_expand_grid(P, Ns, a->n_fac_safe, a->n_sig_safe, a->factors_safe, a->sigmas_safe, s.dt_base_s, s.dt_s,
                                   s.sig_s, s.cand_ofs_s, st));
-    ctx->launch_sorted_dt = true;
+    ctx->launch_sorted_dt = true; ctx->launch_ee_width = a->n_sig_safe;
     rc = fq_launch_solve_ctx(ctx, Ns, 0, P, s.x0_safe, a->xf_safe, a->lim, a->poly_ofs_safe, a->face_ofs_safe, a->Ab_safe,
                              s.cand_ofs_s, mcs, a->max_faces_safe, a->max_poly_faces_safe, s.dt_s, s.sig_s, feas_s, cost_s, nullptr,
                              nullptr, st);

@@ -297,8 +297,10 @@ protected:
   bool ensureContext()
   {
     if (ctx_) return true;
-    if (devices_.size() > 1) return fq_create_multi(&ctx_, (int)devices_.size(), devices_.data()) == 0;
-    return fq_create(&ctx_, device_) == 0;
+    const int rc = devices_.size() > 1 ? fq_create_multi(&ctx_, (int)devices_.size(), devices_.data()) : fq_create(&ctx_, device_);
+    // genNewTraj keeps the first feasible factor (solverGurobi.cpp:445-446): larger factors need not be evaluated
+    if (rc == 0) fq_set_option(ctx_, "sweep_early_exit", 1);
+    return rc == 0;
   }
   void releaseContext() { if (ctx_) { fq_destroy(ctx_); ctx_ = nullptr; } }
   // assignments enumerated for the current (N_, P_): rebuilt only when they change

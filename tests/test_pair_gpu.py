@@ -261,3 +261,32 @@ def test_early_exit_keeps_the_winners(solver):
                 if d >= 0:                                            # everything up to the winning factor is complete
                     assert np.array_equal(fe[j, :d + 1], ff[j, :d + 1])
                     assert np.array_equal(ee["cost_" + k].reshape(n, nf, ns)[j, :d + 1], full["cost_" + k].reshape(n, nf, ns)[j, :d + 1])
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2])
+def test_cpp_driver_several_gpus_through_the_abi(built_lib, tmp_path, n_gpus):
+    """tests/cpp/multi_driver.cpp: one C++ process, fq_create_multi via SolverGurobi::setDevices, fq_replan_pairs on the
+    group == a single-GPU context, bit for bit."""
+    if _n_gpus() < n_gpus:
+        pytest.skip("needs %d GPUs" % n_gpus)
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "multi_driver")
+    libdir = os.path.dirname(built_lib)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "multi_driver.cpp"),
+                           "-o", exe, "-L", libdir, "-lfaster_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, str(n_gpus)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["mismatch"] == 0 and d["world"] == n_gpus and d["whole_solved"] > 0
+
+
+def test_margin_flags_are_reported_not_dropped(solver):
+    import bench
+    w = bench.make_single(dict(bench.SINGLE["cfg2"], seed=9300), 3, capi.dt_initial)
+    args = (w["N"], w["ff"], w["x0"], w["xf"], w["lim"], w["poly_ofs"], w["face_ofs"], w["Ab"], w["cand_ofs"], w["dt"], w["sigma"])
+    f0, near = cr.margin_flags(solver, *args, eps=1e-2)      # a coarse band so that some candidates fall into it
+    assert len(near) == len(f0) == 3 * 1024 and near.any() and not near.all()
+    rep = cr.margin_report(solver, *args)
+    assert rep["candidates"] == 3 * 1024 and rep["within_1e-06"] <= rep["within_1e-05"] <= rep["within_0.0001"]
