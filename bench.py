@@ -260,7 +260,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--corridors", type=int, default=64, help="corridors per GPU per pass (cfg4)")
-    ap.add_argument("--inner", type=int, default=48, help="passes per step")
+    ap.add_argument("--inner", type=int, default=64, help="passes per step")
     ap.add_argument("--ring", type=int, default=8, help="distinct batches a step cycles through")
     ap.add_argument("--ref-corridors", type=int, default=64, help="corridors per step of the CPU arm (the same 64 as one GPU pass)")
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
@@ -664,7 +664,13 @@ def latency_block(solver, capi):
     us, g = med(lambda: solver.gen_new_traj(N_SEG, x0, xf, lim, polys, dts10, sig66, True))
     us_x, ge = med(lambda: solver.gen_new_traj_exact(N_SEG, x0, xf, lim, polys, dts10, True), 40)
     w1 = load_cfg4(0, 1)
-    us_pair, _ = med(lambda: solver.replan_pairs(w1, want_candidates=False), 40)
+    us_pair, rp = med(lambda: solver.replan_pairs(w1, want_candidates=False), 40)
+    # what the drop-in class does (include/solverGurobi.hpp switches the early exit on: only the winner is needed)
+    solver.set_option("sweep_early_exit", 1)
+    us_ee, g_ee = med(lambda: solver.gen_new_traj(N_SEG, x0, xf, lim, polys, dts10, sig66, True))
+    us_x_ee, ge_ee = med(lambda: solver.gen_new_traj_exact(N_SEG, x0, xf, lim, polys, dts10, True), 40)
+    us_pair_ee, rp_ee = med(lambda: solver.replan_pairs(w1, want_candidates=False), 40)
+    solver.set_option("sweep_early_exit", 0)
     import itertools
     pb6 = cr.make_corridor(10000, 3, 6)
     sig729 = np.array(list(itertools.product(range(3), repeat=6)), np.uint8)
@@ -673,6 +679,10 @@ def latency_block(solver, capi):
     out = {"value": us, "what": "fq_gen_new_traj: 10 factors x 66 assignments, N=10, P=3 (a cfg4 forest corridor), host in/out, median",
            "exact_miqp": us_x, "exact_nodes": int(ge["nodes"]),
            "exact_same_winner": bool(ge["dt_index"] == g["dt_index"] and abs(ge["cost"] - g["cost"]) <= 1e-9 * max(1.0, g["cost"])),
+           "early_exit": {"value": us_ee, "exact_miqp": us_x_ee, "chained_pair_one_corridor": us_pair_ee,
+                          "same_winners": bool(g_ee["dt_index"] == g["dt_index"] and g_ee["cost"] == g["cost"] and ge_ee["cost"] == ge["cost"] and
+                                               rp_ee["results"].tobytes() == rp["results"].tobytes()),
+                          "what": "option sweep_early_exit = 1 (the drop-in class's setting): factors beyond the first feasible one are not evaluated"},
            "chained_pair_one_corridor": us_pair, "chained_pair_what": "fq_replan_pairs, 1 corridor: whole 16x64 -> R -> safe 16x64, winners' coefficients back",
            "shipped_yaml_N6_P3_all_729_assignments": us6}
     try:

@@ -114,6 +114,8 @@ extern "C" void fq_destroy(fq_ctx* ctx)
 extern "C" int fq_set_option(fq_ctx* ctx, const char* key, int value)
 {
   if (!ctx || !key) return FQ_E_ARG;
+  for (fq_ctx* p : ctx->peers)                     // a multi-GPU group: every member gets the option
+    if (int rc = fq_set_option(p, key, value)) { ctx->err = p->err; return rc; }
   if (std::string(key) == "force_generic_kernel") { ctx->force_generic = value != 0; return 0; }
   if (std::string(key) == "throughput_slices") { ctx->throughput_slices = value > 0 && value <= 64 ? value : 0; return 0; }
   if (std::string(key) == "max_faces_per_polytope") { ctx->max_poly_faces_hint = value > 0 ? value : 0; return 0; }

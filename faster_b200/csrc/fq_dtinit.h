@@ -93,31 +93,42 @@ FQ_HD double min_positive(const double* v, int n)
   return best;
 }
 
-// getDTInitial: per axis the minimum time under the velocity, acceleration and jerk limit alone; float temporaries
-// exactly where the reference has them (:662-670); the result is max over axes and limits divided by N, in float (:751)
-FQ_HD double dt_initial(const double* x0, const double* xf, const double* lim, int N)
+// getDTInitial, one axis: the minimum time under the velocity, acceleration and jerk limit alone; float temporaries exactly
+// where the reference has them (:662-670).  Returns max(t_v, t_a, t_j) of axis i as float.
+FQ_HD float dt_axis(const double* x0, const double* xf, const double* lim, int i)
 {
   const double v_max = lim[0], a_max = lim[1], j_max = lim[2];
-  float worst = 0;
-  for (int i = 0; i < 3; i++)
-  {
-    const double dp = FQ_SUB(xf[i], x0[i]);
-    const float t_v = (float)FQ_DIV(fabs(dp), v_max);                    // :672-674
-    const float jerk = (float)FQ_MUL(copysign(1.0, dp), j_max);          // :679-681
-    const float accel = (float)FQ_MUL(copysign(1.0, dp), a_max);         // :718-720
-    const float a0 = (float)x0[6 + i], v0 = (float)x0[3 + i];            // :682-687
-    double r[3];
-    int k = roots3(FQ_SUB(x0[i], xf[i]), (double)v0, FQ_DIV((double)a0, 2.0), FQ_DIV((double)jerk, 6.0), r);   // :691-713
-    const float t_j = (float)min_positive(r, k);
-    k = roots2(FQ_SUB(x0[i], xf[i]), (double)v0, FQ_MUL(0.5, (double)accel), r);                               // :724-746
-    const float t_a = (float)min_positive(r, k);
-    const float m1 = t_a > t_j ? t_a : t_j;
-    const float m2 = t_v > m1 ? t_v : m1;
-    worst = worst > m2 ? worst : m2;
-  }
+  const double dp = FQ_SUB(xf[i], x0[i]);
+  const float t_v = (float)FQ_DIV(fabs(dp), v_max);                    // :672-674
+  const float jerk = (float)FQ_MUL(copysign(1.0, dp), j_max);          // :679-681
+  const float accel = (float)FQ_MUL(copysign(1.0, dp), a_max);         // :718-720
+  const float a0 = (float)x0[6 + i], v0 = (float)x0[3 + i];            // :682-687
+  double r[3];
+  int k = roots3(FQ_SUB(x0[i], xf[i]), (double)v0, FQ_DIV((double)a0, 2.0), FQ_DIV((double)jerk, 6.0), r);   // :691-713
+  const float t_j = (float)min_positive(r, k);
+  k = roots2(FQ_SUB(x0[i], xf[i]), (double)v0, FQ_MUL(0.5, (double)accel), r);                               // :724-746
+  const float t_a = (float)min_positive(r, k);
+  const float m1 = t_a > t_j ? t_a : t_j;
+  return t_v > m1 ? t_v : m1;
+}
+
+// the result is the max over axes and limits divided by N, in float (:751)
+FQ_HD double dt_from_worst(float worst, int N)
+{
   double dt = (double)(worst / (float)N);                                // float / int (:751)
   if (dt > 10000) dt = 0;                                                // :752-756
   return dt;
+}
+
+FQ_HD double dt_initial(const double* x0, const double* xf, const double* lim, int N)
+{
+  float worst = 0;
+  for (int i = 0; i < 3; i++)
+  {
+    const float m2 = dt_axis(x0, xf, lim, i);
+    worst = worst > m2 ? worst : m2;
+  }
+  return dt_from_worst(worst, N);
 }
 
 // resetX (:382-388): (int)(N_)*dt_/DC truncated to int, at least 2

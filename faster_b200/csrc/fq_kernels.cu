@@ -628,7 +628,7 @@ cudaError_t fq_launch_dtbase(int n_prob, int N, double DC, const double* x0, con
                              double* dt_base, cudaStream_t stream)
 {
   if (n_prob <= 0) return cudaSuccess;
-  fqp::fq_dtbase_kernel<<<(n_prob + 127) / 128, 128, 0, stream>>>(n_prob, N, DC, x0, xf, lim, dt_base);
+  fqp::fq_dtbase_kernel<<<(4 * n_prob + 127) / 128, 128, 0, stream>>>(n_prob, N, DC, x0, xf, lim, dt_base);
   return cudaGetLastError();
 }
 

@@ -12,15 +12,24 @@ namespace fqp
 // problem whose whole sweep found nothing) give NaN, which makes every candidate of the problem "not solved".
 __global__ void fq_dtbase_kernel(int n_prob, int N, double DC, const double* __restrict__ x0, const double* __restrict__ xf,
                                  const double* __restrict__ lim, double* __restrict__ dt_base)
-{
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_prob) return;
+{ // four lanes per problem: one per axis (the cubic / quadratic root finding is the long part), the fourth idles
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = tid >> 2, ax = tid & 3;
+  const bool live = j < n_prob;
   double a[9], b[9], l[3];
-  bool ok = true;
-  for (int i = 0; i < 9; i++) { a[i] = x0[j * 9 + i]; b[i] = xf[j * 9 + i]; ok = ok && isfinite(a[i]) && isfinite(b[i]); }
-  for (int i = 0; i < 3; i++) { l[i] = lim[j * 3 + i]; ok = ok && l[i] > 0 && isfinite(l[i]); }
+  bool ok = live;
+  float worst = 0;
+  if (live)
+  {
+    for (int i = 0; i < 9; i++) { a[i] = x0[j * 9 + i]; b[i] = xf[j * 9 + i]; ok = ok && isfinite(a[i]) && isfinite(b[i]); }
+    for (int i = 0; i < 3; i++) { l[i] = lim[j * 3 + i]; ok = ok && l[i] > 0 && isfinite(l[i]); }
+    if (ok && ax < 3) worst = fqdt::dt_axis(a, b, l, ax);
+  }
+  worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, 1));
+  worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, 2));
+  if (!live || ax != 0) return;
   if (!ok) { dt_base[j] = __longlong_as_double(0x7ff8000000000000ll); return; }
-  const double dti = fqdt::dt_initial(a, b, l, N);
+  const double dti = fqdt::dt_from_worst(worst, N);
   const double floor2 = FQ_MUL(2.0, DC);
   dt_base[j] = dti > floor2 ? dti : floor2;            // std::max(getDTInitial(), 2 * DC)
 }

@@ -53,6 +53,8 @@ int main(int argc, char** argv)
   if (!g) { std::printf("fq_create_multi: %s\n", fq_last_error(nullptr)); return 4; }
   int rank = -1, world = -1, ver = 0;
   fq_comm_info(g, &rank, &world, &ver);
+  // the class switches the early exit on (only winners matter to genNewTraj); this comparison wants every candidate
+  if (fq_set_option(g, "sweep_early_exit", 0) != 0) { std::printf("option: %s\n", fq_last_error(g)); return 6; }
   a.results = rn.data(); a.feasible_whole = fn.data(); a.cost_whole = cn.data();
   if (fq_replan_pairs(g, &a) != 0) { std::printf("group: %s\n", fq_last_error(g)); return 5; }
   int bad = world != n_gpus;

@@ -225,8 +225,13 @@ def test_two_ranks_one_process_each(tmp_path):
     uid = tmp_path / "uid.bin"
     procs = [subprocess.Popen([sys.executable, script, str(r), "2", str(uid), str(tmp_path / ("out%d.npy" % r))], cwd=root)
              for r in range(2)]
-    for p in procs:
-        assert p.wait(timeout=300) == 0
+    try:
+        for p in procs:
+            assert p.wait(timeout=300) == 0
+    finally:
+        for p in procs:                                   # a rank that died leaves its peer waiting inside NCCL: do not leak it
+            if p.poll() is None:
+                p.kill()
     a = np.load(tmp_path / "out0.npy"); b = np.load(tmp_path / "out1.npy")
     assert a.tobytes() == b.tobytes()                     # every rank holds every corridor's record
     s = capi.Solver(0)
