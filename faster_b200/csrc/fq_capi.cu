@@ -661,7 +661,12 @@ int gen_new_traj_impl(fq_ctx* ctx, int N, int force_final, const double* x0, con
   cudaStream_t st = ctx->stream;
   char* din = (char*)ctx->d_in.p;
   char* dout = (char*)ctx->d_out.p;
+  cudaEvent_t tev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };      // FQ_TRACE: device-side phase times
+  if (tr.on)
+    for (auto& e : tev) cudaEventCreate(&e);
+  if (tr.on) cudaEventRecord(tev[0], st);
   FQ_CUDA(cudaMemcpyAsync(din, hi, in_bytes, cudaMemcpyHostToDevice, st));
+  if (tr.on) cudaEventRecord(tev[1], st);
   {
     bool asc = true;
     for (int d = 1; d < n_dt; d++) asc = asc && dts[d] >= dts[d - 1];
@@ -673,6 +678,7 @@ int gen_new_traj_impl(fq_ctx* ctx, int N, int force_final, const double* x0, con
                         (const double*)(din + odt), (const uint8_t*)(din + osig), (uint8_t*)(dout + ofeas),
                         (double*)(dout + ocost), (double*)(dout + ocoef), nullptr, st);
   if (rc) return rc;
+  if (tr.on) cudaEventRecord(tev[2], st);
   FqSelectArgs sa;
   sa.n_dt = n_dt; sa.n_sigma = n_sigma; sa.N = N;
   sa.feasible = (const uint8_t*)(dout + ofeas); sa.cost = (const double*)(dout + ocost);
@@ -691,10 +697,21 @@ int gen_new_traj_impl(fq_ctx* ctx, int N, int force_final, const double* x0, con
     FQ_CUDA(fq_launch_fill(fa, st));
     tail_bytes = 4 * sizeof(int) + sizeof(double) * 12 * (size_t)max_samples;
   }
+  if (tr.on) cudaEventRecord(tev[3], st);
   FQ_CUDA(cudaMemcpyAsync(ho, dout + owin, win_bytes + tail_bytes, cudaMemcpyDeviceToHost, st));
+  if (tr.on) cudaEventRecord(tev[4], st);
   tr.mark("enqueue");
   FQ_CUDA(cudaStreamSynchronize(st));
   tr.mark("wait");
+  if (tr.on)
+  {
+    float a = 0, b = 0, c = 0, d = 0;
+    cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]);
+    cudaEventElapsedTime(&c, tev[2], tev[3]); cudaEventElapsedTime(&d, tev[3], tev[4]);
+    std::fprintf(stderr, "[fq trace] device: h2d %.1f us, counters+solve %.1f us, select(+fill) %.1f us, d2h %.1f us\n", a * 1e3, b * 1e3,
+                 c * 1e3, d * 1e3);
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
   static_assert(sizeof(double) == 8, "layout");
   const int* idx = (const int*)(ho + win_bytes);
   const double* win = (const double*)ho;

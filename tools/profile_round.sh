@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 BENCH="python bench.py --steps 2 --warmup 1 --inner 4 --quick --single-stream"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$tag.csv \
     $BENCH > gpurun_out/ncu_list_$tag.log 2>&1
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:fq_solve_kernel_t -s 6 -c 2 -f -o gpurun_out/prof_$tag \
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:fq_solve_kernel_t -s 6 -c 3 -f -o gpurun_out/prof_$tag \
     $BENCH > gpurun_out/ncu_full_$tag.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:fq_solve_kernel_t -s 1 -c 1 -f -o gpurun_out/prof_cfg5_$tag \
     python bench.py --config cfg5 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_cfg5_$tag.log 2>&1
