@@ -200,7 +200,17 @@ int fq_launch_solve_ctx(fq_ctx* ctx, int N, int force_final, int n_prob, const d
     a.memo_salt = ctx->memo_salt;
   }
 #endif
-  FQ_CUDA(fq_launch_solve(a, max_cand, stream, counters, ctx->sm_count, env_generic || ctx->force_generic || a.cert != nullptr));
+  a.sweep_done = nullptr; a.sweep_n_sigma = 0; a.sweep_idx = nullptr; a.sweep_win = nullptr;
+  const bool generic = env_generic || ctx->force_generic || a.cert != nullptr;
+  if (ctx->launch_sweep_n_sigma > 0 && n_prob == 1 && d_coeffs && !generic)
+  {
+    a.sweep_done = counters + n_prob; a.sweep_n_sigma = ctx->launch_sweep_n_sigma;
+    a.sweep_idx = ctx->launch_sweep_idx; a.sweep_win = ctx->launch_sweep_win;
+  }
+  ctx->launch_sweep_n_sigma = 0;
+  bool spec = false;
+  FQ_CUDA(fq_launch_solve(a, max_cand, stream, counters, ctx->sm_count, generic, &spec));
+  ctx->last_launch_tail = spec && a.sweep_done != nullptr;
   return 0;
 }
 namespace
@@ -672,21 +682,34 @@ int gen_new_traj_impl(fq_ctx* ctx, int N, int force_final, const double* x0, con
     for (int d = 1; d < n_dt; d++) asc = asc && dts[d] >= dts[d - 1];
     ctx->launch_sorted_dt = asc; ctx->launch_ee_width = asc ? n_sigma : 0;
   }
+  char* ho = (char*)ctx->h_out.p;
+  const size_t win_bytes = sizeof(double) * (1 + 12 * (size_t)N);
+  if (!samples)
+  { // the last warp to finish selects the winner and writes the record (cost, coefficients, indices) into this pinned,
+    // device-visible host buffer: no selection launch and no device-to-host copy on the latency path
+    void *dwin = nullptr;
+    if (cudaHostGetDevicePointer(&dwin, ho, 0) == cudaSuccess)
+    {
+      ctx->launch_sweep_n_sigma = n_sigma;
+      ctx->launch_sweep_win = (double*)dwin;
+      ctx->launch_sweep_idx = (int*)((char*)dwin + win_bytes);
+      ((int*)(ho + win_bytes))[0] = -2;               // overwritten by the kernel
+    }
+  }
   int rc = launch_solve(ctx, N, force_final, 1, (const double*)(din + ox0), (const double*)(din + oxf),
                         (const double*)(din + olim), (const int*)(din + opo), (const int*)(din + ofo),
                         (const double*)(din + oAb), (const int*)(din + oco), n_cand, n_face, max_pf,
                         (const double*)(din + odt), (const uint8_t*)(din + osig), (uint8_t*)(dout + ofeas),
                         (double*)(dout + ocost), (double*)(dout + ocoef), nullptr, st);
   if (rc) return rc;
+  const bool tail = ctx->last_launch_tail;
   if (tr.on) cudaEventRecord(tev[2], st);
   FqSelectArgs sa;
   sa.n_dt = n_dt; sa.n_sigma = n_sigma; sa.N = N;
   sa.feasible = (const uint8_t*)(dout + ofeas); sa.cost = (const double*)(dout + ocost);
   sa.coeffs = (const double*)(dout + ocoef);
   sa.out_idx = (int*)(dout + oidx); sa.out_cost = (double*)(dout + owin); sa.out_coeffs = (double*)(dout + owin) + 1;
-  FQ_CUDA(fq_launch_select(sa, st));
-  char* ho = (char*)ctx->h_out.p;
-  const size_t win_bytes = sizeof(double) * (1 + 12 * (size_t)N);
+  if (!tail) FQ_CUDA(fq_launch_select(sa, st));
   size_t tail_bytes = 2 * sizeof(int);
   if (samples)
   { // fillX on the device, chained on the same stream; samples travel back with the winner record
@@ -698,7 +721,7 @@ int gen_new_traj_impl(fq_ctx* ctx, int N, int force_final, const double* x0, con
     tail_bytes = 4 * sizeof(int) + sizeof(double) * 12 * (size_t)max_samples;
   }
   if (tr.on) cudaEventRecord(tev[3], st);
-  FQ_CUDA(cudaMemcpyAsync(ho, dout + owin, win_bytes + tail_bytes, cudaMemcpyDeviceToHost, st));
+  if (!tail) FQ_CUDA(cudaMemcpyAsync(ho, dout + owin, win_bytes + tail_bytes, cudaMemcpyDeviceToHost, st));
   if (tr.on) cudaEventRecord(tev[4], st);
   tr.mark("enqueue");
   FQ_CUDA(cudaStreamSynchronize(st));
@@ -715,6 +738,7 @@ int gen_new_traj_impl(fq_ctx* ctx, int N, int force_final, const double* x0, con
   static_assert(sizeof(double) == 8, "layout");
   const int* idx = (const int*)(ho + win_bytes);
   const double* win = (const double*)ho;
+  if (tail && idx[0] == -2) return fail(ctx, FQ_E_CUDA, "internal: the sweep finished without its selection");
   if (dt_index) *dt_index = idx[0];
   if (sigma_index) *sigma_index = idx[1];
   if (n_samples) *n_samples = 0;
@@ -889,7 +913,7 @@ extern "C" int fq_gen_new_traj_exact(fq_ctx* ctx, int N, int force_final, const 
     L.k.poly_ofs = (const int*)(db + opo); L.k.face_ofs = (const int*)(db + ofo); L.k.Ab = (const double*)(db + oAb);
     L.k.max_faces = n_face; L.k.item_cap = N * max_pf; L.k.cand_ofs = nullptr; L.k.dt = nullptr; L.k.sigma = nullptr;
     L.k.feasible = nullptr; L.k.cost = nullptr; L.k.coeffs = nullptr; L.k.iters = nullptr; L.k.row_tol = ctx->row_tol;
-    L.k.memo = nullptr; L.k.memo_salt = 0; L.k.cert = nullptr; L.k.cert_stride = 0; L.k.first_feasible = nullptr; L.k.sorted_dt = 0; L.k.ee_width = 0;
+    L.k.memo = nullptr; L.k.memo_salt = 0; L.k.cert = nullptr; L.k.cert_stride = 0; L.k.first_feasible = nullptr; L.k.sorted_dt = 0; L.k.ee_width = 0; L.k.sweep_done = nullptr; L.k.sweep_n_sigma = 0; L.k.sweep_idx = nullptr; L.k.sweep_win = nullptr;
     L.n_dt = n_dt; L.P = P; L.dts = (const double*)(db + odts); L.roots = (const int*)(db + oroot);
     L.incumbent = (unsigned long long*)(db + oinc); L.leaves = db + oleaf; L.n_leaves = (int*)(db + ocnt) + 1;
     L.leaf_cap = leaf_cap; L.flags = (int*)(db + ocnt) + 2; L.n_children = (int*)(db + ocnt); L.cap = cap;

@@ -75,6 +75,11 @@ struct fq_ctx
   bool early_exit = false;        // option "sweep_early_exit": candidates that cannot win genNewTraj's selection are skipped
   bool launch_sorted_dt = false;  // set by the chained replan for its next launch: candidate lists are in ascending dt order
   int launch_ee_width = 0;        // ... and hold this many candidates per time allocation
+  // single-problem sweep with the selection in the solve kernel's tail (consumed by the next launch):
+  int launch_sweep_n_sigma = 0;   // > 0: requested
+  int* launch_sweep_idx = nullptr;       // device-visible (host-mapped) outputs
+  double* launch_sweep_win = nullptr;
+  bool last_launch_tail = false;  // the last launch did run the tail selection (specialised kernel)
   unsigned long long* d_first = nullptr;   // ring (as d_counters) of per-problem "smallest feasible dt so far"
   double* cert_out = nullptr;     // fq_solve_batch_cert: device buffer the generic kernel writes certificates into
   int cert_stride = 0;

@@ -459,20 +459,29 @@ __global__ void __launch_bounds__(256) fq_select_kernel(const FqSelectArgs a)
     if (threadIdx.x == 0) { a.out_idx[0] = -1; a.out_idx[1] = -1; a.out_cost[0] = INFINITY; }
     return;
   }
-  // costs are non-negative doubles: their bit patterns order like unsigned integers.  Pack (cost, index).
+  // costs are non-negative doubles: their bit patterns order like unsigned integers.  Exact two-step reduction: the
+  // minimum cost, then the lowest assignment index that attains it (ties are exact cost ties).
   unsigned long long best = ~0ull;
   for (int s = threadIdx.x; s < a.n_sigma; s += blockDim.x)
   {
     const int i = dtw * a.n_sigma + s;
     if (!a.feasible[i]) continue;
-    // keep the top 44 bits of the cost and the index in the low 20 (ties and sub-1e-13 differences -> lowest index)
     const unsigned long long bits = (unsigned long long)__double_as_longlong(a.cost[i]);
-    const unsigned long long k = (bits & ~0xfffffull) | (unsigned long long)(s & 0xfffff);
-    if (k < best) best = k;
+    if (bits < best) best = bits;
   }
   if (best != ~0ull) atomicMin(&s_best, best);
   __syncthreads();
-  const int sw = (int)(s_best & 0xfffffull);
+  const unsigned long long cb = s_best;
+  __shared__ int s_sig;
+  if (threadIdx.x == 0) s_sig = 0x7fffffff;
+  __syncthreads();
+  for (int s = threadIdx.x; s < a.n_sigma; s += blockDim.x)
+  {
+    const int i = dtw * a.n_sigma + s;
+    if (a.feasible[i] && (unsigned long long)__double_as_longlong(a.cost[i]) == cb) { atomicMin(&s_sig, s); break; }
+  }
+  __syncthreads();
+  const int sw = s_sig;
   const int win = dtw * a.n_sigma + sw;
   if (threadIdx.x == 0) { a.out_idx[0] = dtw; a.out_idx[1] = sw; a.out_cost[0] = a.cost[win]; }
   if (a.coeffs && a.out_coeffs)
@@ -545,8 +554,9 @@ bool fq_has_specialised(int N, int force_final, int max_faces)
 }
 
 cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream, int* counters, int sm_count,
-                            bool force_generic)
+                            bool force_generic, bool* used_specialised)
 {
+  if (used_specialised) *used_specialised = false;
   if (a.n_prob <= 0 || max_cand_per_prob <= 0) return cudaSuccess;
   if (!force_generic && fq_has_specialised(a.N, a.force_final, a.max_faces))
   {
@@ -566,7 +576,7 @@ cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaSt
 #undef FQ_CASE
     // cudaErrorInvalidConfiguration: the problem (very many faces per polytope) does not fit the specialised kernel's
     // shared-memory layout -> the size-generic kernel below takes it
-    if (e != cudaErrorInvalidConfiguration) return e;
+    if (e != cudaErrorInvalidConfiguration) { if (used_specialised) *used_specialised = e == cudaSuccess; return e; }
   }
   const size_t smem = fq_solve_smem_bytes(a);
   {  // per-device attribute; cheap enough to set on every launch (contexts on several GPUs share this code)

@@ -66,6 +66,13 @@ struct FqKernelArgs
   unsigned long long* first_feasible;
   int sorted_dt;         // candidates of every problem are in ascending dt order (the chained replan's grids)
   int ee_width;          // candidates per time allocation (0: unknown); sizes the grid of an early-exit sweep
+  // single-problem sweeps (fq_gen_new_traj*): the warp that finishes the LAST candidate runs genNewTraj's selection itself
+  // and writes the winner record straight into mapped host memory -- no selection launch, no device-to-host copy.
+  // sweep_done = counter of finished candidates (zeroed with the claim counters), or nullptr.
+  int* sweep_done;
+  int sweep_n_sigma;     // candidates per time allocation (the list is dt-major)
+  int* sweep_idx;        // out (host-mapped): [0] dt index (-1 none), [1] sigma index
+  double* sweep_win;     // out (host-mapped): [0] cost, [1 .. 12N] coefficients of the winner (a.coeffs must be set)
   // size-generic kernel only (fq_solve_batch_cert): per infeasible candidate, [n, violation, (row id, multiplier) x n]
   double* cert;
   int cert_stride;
@@ -121,7 +128,7 @@ size_t fq_solve_smem_bytes(const FqKernelArgs& a);
 // `counters`: a.n_prob ints of device memory owned by the caller's context (per-problem claim counters of the
 // persistent kernel; zeroed by the launch on `stream`)
 cudaError_t fq_launch_solve(const FqKernelArgs& a, int max_cand_per_prob, cudaStream_t stream, int* counters, int sm_count,
-                            bool force_generic = false);
+                            bool force_generic = false, bool* used_specialised = nullptr);
 bool fq_has_specialised(int N, int force_final, int max_faces);
 cudaError_t fq_launch_select(const FqSelectArgs& a, cudaStream_t stream);
 

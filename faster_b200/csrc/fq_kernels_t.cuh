@@ -906,6 +906,46 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
   __syncwarp();
 }
 
+// genNewTraj's selection (solverGurobi.cpp:445-472) by ONE warp, for a single-problem sweep whose candidates are dt-major
+// with n_sigma assignments per time allocation: first time allocation with a feasible assignment, then the minimum cost,
+// then the lowest assignment index (exact).  Writes the winner record to (host-mapped) memory.
+template <int N_>
+__device__ void sweep_tail_select(const FqKernelArgs& a, int c_begin, int count, int lane)
+{
+  const int ns = a.sweep_n_sigma;
+  int first = 0x7fffffff;
+  for (int i = lane; i < count; i += 32)
+    if (a.feasible[c_begin + i]) { first = i; break; }
+  first = __reduce_min_sync(FULL, first);
+  if (first == 0x7fffffff)
+  {
+    if (lane == 0) { a.sweep_idx[0] = -1; a.sweep_idx[1] = -1; a.sweep_win[0] = INFINITY; }
+    __threadfence_system();
+    return;
+  }
+  const int dtw = first / ns;
+  unsigned long long best = ~0ull;
+  for (int s = lane; s < ns; s += 32)
+  {
+    const int i = c_begin + dtw * ns + s;
+    if (a.feasible[i]) { const unsigned long long b = (unsigned long long)__double_as_longlong(a.cost[i]); best = b < best ? b : best; }
+  }
+  unsigned hi = __reduce_min_sync(FULL, (unsigned)(best >> 32));
+  unsigned lo = __reduce_min_sync(FULL, (unsigned)(best >> 32) == hi ? (unsigned)best : 0xffffffffu);
+  const unsigned long long cb = (unsigned long long)hi << 32 | lo;
+  int sw = 0x7fffffff;
+  for (int s = lane; s < ns; s += 32)
+  {
+    const int i = c_begin + dtw * ns + s;
+    if (a.feasible[i] && (unsigned long long)__double_as_longlong(a.cost[i]) == cb) { sw = s; break; }
+  }
+  sw = __reduce_min_sync(FULL, sw);
+  const int win = c_begin + dtw * ns + sw;
+  if (lane == 0) { a.sweep_idx[0] = dtw; a.sweep_idx[1] = sw; a.sweep_win[0] = a.cost[win]; }
+  for (int i = lane; i < 12 * N_; i += 32) a.sweep_win[1 + i] = a.coeffs[(size_t)win * 12 * N_ + i];
+  __threadfence_system();
+}
+
 // Persistent CTAs.  counters[j] = next unclaimed candidate of problem j (zeroed before the launch).  A CTA (or, with
 // FQ_WARP_ADOPT, every warp on its own) adopts a problem that still has unclaimed candidates (scanning from its own start
 // so the adopters spread over the problems), stages the problem's polytope rows once, and claims candidates one by one
@@ -1015,6 +1055,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
       if (lane == 0) cn = atomicAdd(counters + prob, 1);
       // claims run from the end of the list (long solves first); with the early exit from its start (smallest dt first)
       const int cand = c_begin + (ee ? c : count - 1 - c);
+      int n_done = 1;                                // candidates this iteration finishes (more when it drains the list)
       bool skip = false;
       if (ee)
       {
@@ -1029,6 +1070,7 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
           int old = 0;
           if (lane == 0) old = atomicExch(counters + prob, count + 1);
           old = __shfl_sync(FULL, old, 0);
+          if (old < count) n_done += count - old;
           if (old < count)
             for (int i = c_begin + old + lane; i < c_begin + count; i += 32)
             {
@@ -1044,6 +1086,18 @@ __global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOL
         }
         if (a.coeffs)
           for (int idx = lane; idx < 12 * D::N; idx += 32) a.coeffs[(size_t)cand * D::N * 12 + idx] = 0.0;
+      }
+      if (a.sweep_done)
+      { // single-problem sweep: whoever finishes the last candidate selects the winner (all results are published first)
+        __threadfence();
+        int fin = 0;
+        if (lane == 0) fin = atomicAdd(a.sweep_done, n_done) + n_done;
+        fin = __shfl_sync(FULL, fin, 0);
+        if (fin == count)
+        {
+          __threadfence();
+          sweep_tail_select<N_>(a, c_begin, count, lane);
+        }
       }
       c = __shfl_sync(FULL, cn, 0);
     }
@@ -1165,7 +1219,7 @@ cudaError_t launch_t(const FqKernelArgs& a, long long total_cand_hint, cudaStrea
     if (grid > cap) grid = cap;
   }
   if (grid < 1) grid = 1;
-  e = cudaMemsetAsync(counters, 0, sizeof(int) * (size_t)a.n_prob, stream);
+  e = cudaMemsetAsync(counters, 0, sizeof(int) * ((size_t)a.n_prob + (a.sweep_done ? 1 : 0)), stream);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)grid, W * 32, smem, stream>>>(a, counters);
   return cudaGetLastError();
