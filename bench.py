@@ -174,6 +174,31 @@ def cfg4_config(world, C):
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm
 # ----------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    """Threads the CPU arm may really use: the scheduler affinity and the cgroup CPU quota of this container, not the
+    machine's core count (a 1-GPU slice of an 8-GPU host gets a slice of its cores)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
+
+
 CPU_NOTE = ("tuned CPU port of the GPU kernel's algorithm (oracle/fq_cpu_port.c: plan tables, normalised pivoting, thin "
             "factorisation, persistent thread pool with dynamic claiming, AVX2) driving the same chain; Gurobi itself is unavailable")
 
@@ -202,7 +227,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     from oracle import pyoracle as po, pair_oracle
     po.build()
     n_s = max(1, args.ref_corridors)
@@ -227,7 +252,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port-tuned",
                              "sample": "%d corridors x 1024 pairs of the cfg4 fixture per step" % n_s, "note": CPU_NOTE,
                              "step_ms_p50_p99": [float(np.percentile(step_s, 50) * 1e3), float(np.percentile(step_s, 99) * 1e3)],
-                             "literal_restatement_pairs_per_s": lit},
+                             "literal_restatement_pairs_per_s": lit, "os_cpu_count": os.cpu_count()},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -501,11 +526,11 @@ def main():
     if rank == 0:
         line["replan_latency_us"] = latency_block(e2e_solvers[0], capi)
     if rank == 0 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         rate, sample = cpu_pair_rate(args.ref_corridors, threads, args.cpu_seconds)
         lit, _ = cpu_pair_rate(max(1, args.ref_corridors // 8), threads, 2.0, fast=False)
         line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port-tuned", "sample": sample,
-                                "note": CPU_NOTE, "literal_restatement_pairs_per_s": lit}
+                                "note": CPU_NOTE, "literal_restatement_pairs_per_s": lit, "os_cpu_count": os.cpu_count()}
     if world == 1 and not args.no_other_configs:
         line["other_configs"] = {}
         for name in ("cfg2", "cfg3", "cfg5"):
@@ -793,7 +818,7 @@ def bench_single(args, name, torch, capi, dev, local, world, rank, barrier, main
         nc_cpu = min(C, max(1, 65536 // w["cand"]))             # the tuned CPU port on about 65 536 candidates per pass
         sub = (w["N"], w["ff"], w["x0"][:nc_cpu], w["xf"][:nc_cpu], w["lim"][:nc_cpu], w["poly_ofs"][:nc_cpu + 1],
                w["face_ofs"][:w["poly_ofs"][nc_cpu] + 1], w["Ab"][:w["face_ofs"][w["poly_ofs"][nc_cpu]]], w["cand_ofs"][:nc_cpu + 1],
-               w["dt"][:nc_cpu * w["cand"]], w["sigma"][:nc_cpu * w["cand"]], os.cpu_count() or 1)
+               w["dt"][:nc_cpu * w["cand"]], w["sigma"][:nc_cpu * w["cand"]], host_threads())
         fp, _ = po.solve_multi_port(*sub)
         out["parity"]["tuned_cpu_port_flag_mismatches_vs_gpu"] = int((fp != feas[:nc_cpu * w["cand"]].cpu().numpy()).sum())
         t0 = time.perf_counter()
@@ -801,7 +826,7 @@ def bench_single(args, name, torch, capi, dev, local, world, rank, barrier, main
         while time.perf_counter() - t0 < (2.0 if not main_line else args.cpu_seconds):
             po.solve_multi_port(*sub)
             reps += 1
-        out["cpu_baseline"] = {"value": reps * nc_cpu * w["cand"] / (time.perf_counter() - t0), "unit": "candidates/s", "cores": os.cpu_count() or 1,
+        out["cpu_baseline"] = {"value": reps * nc_cpu * w["cand"] / (time.perf_counter() - t0), "unit": "candidates/s", "cores": host_threads(),
                                "kind": "port-tuned", "sample": "%d corridor(s) x %d candidates, %d passes" % (nc_cpu, w["cand"], reps)}
     solver.close()
     return out

@@ -27,6 +27,9 @@
 #define FQ_SPLIT_ROWS 0       // 1: staged polytope rows as two arrays of 16-byte halves ([Ax Ay] and [Az b+tol]): both loads of
                               // the row scan become bank-conflict free (rows 32 bytes apart give a two-way conflict)
 #endif
+#ifndef FQ_SCAN_UNROLL
+#define FQ_SCAN_UNROLL 1       // unroll factor of the corridor-row scan (more loads in flight per warp)
+#endif
 #define FQ_EPS_DEP 1e-18      // squared sine below which a new normal counts as dependent on the active set
 #define FQ_ZZ_FLOOR 1e-30
 #define FQ_MAX_ITERS 400

@@ -405,6 +405,8 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
   while (status == -2)
   {
     // ================= most violated corridor row (box rows were checked by update_Y) =================
+    constexpr int SCAN_UNROLL = FQ_SCAN_UNROLL;
+#pragma unroll SCAN_UNROLL
     for (int i = lane; i < total_rows; i += 32)
     {
       const unsigned item = m.items[i];
