@@ -292,6 +292,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--single-stream", action="store_true", help="all chains on one stream / context (no overlap of consecutive batches)")
+    ap.add_argument("--contexts", type=int, default=2, help="solver contexts / streams the chains of consecutive batches rotate over")
     ap.add_argument("--quick", action="store_true", help="profiling runs: main timing only")
     ap.add_argument("--no-memo", action="store_true", help="A/B: switch the infeasibility-certificate memo off (option cert_memo = 0)")
     args = ap.parse_args()
@@ -325,7 +326,7 @@ def main():
         return
 
     # ---- contexts: two (chains of consecutive batches overlap on two streams), each attached to the communicator
-    n_ctx = 1 if args.single_stream else 2
+    n_ctx = 1 if args.single_stream else max(1, args.contexts)
     solvers = [capi.Solver(local) for _ in range(n_ctx)]
     if args.no_memo:
         for sv in solvers:
@@ -339,6 +340,7 @@ def main():
     tstream = torch.cuda.Stream(device=dev)                  # timing stream: forks to / joins from the chain streams
     torch.cuda.set_stream(tstream)
     C, ring, inner = args.corridors, args.ring, args.inner
+    ring = ((ring + n_ctx - 1) // n_ctx) * n_ctx            # a batch always meets the same context / stream
     n_fix = 512
     batches = [PairBatch(load_cfg4(((rank * ring + b) * C) % n_fix, C), dev, torch, capi, gather_world=world if world > 1 else 0)
                for b in range(ring)]
@@ -448,8 +450,8 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": cfg4_config(world, C),
                 "run": {"passes_per_step": inner, "distinct_batches": ring, "certificate_memo": not args.no_memo,
-                        "streams": "one" if args.single_stream else
-                                   "two contexts / streams: the chains of consecutive batches overlap (the tail of one fills with the next)"},
+                        "streams": "one" if n_ctx == 1 else
+                                   "%d contexts / streams: the chains of consecutive batches overlap (the tail of one fills with the next)" % n_ctx},
                 "timed_region_s": total_ms * 1e-3,
                 "step_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)),
                             "min": float(np.min(step_ms)), "max": float(np.max(step_ms)), "note": "rank 0's steps"},
