@@ -292,7 +292,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--single-stream", action="store_true", help="all chains on one stream / context (no overlap of consecutive batches)")
-    ap.add_argument("--contexts", type=int, default=2, help="solver contexts / streams the chains of consecutive batches rotate over")
+    ap.add_argument("--contexts", type=int, default=3, help="solver contexts / streams the chains of consecutive batches rotate over")
     ap.add_argument("--quick", action="store_true", help="profiling runs: main timing only")
     ap.add_argument("--no-memo", action="store_true", help="A/B: switch the infeasibility-certificate memo off (option cert_memo = 0)")
     args = ap.parse_args()
@@ -396,7 +396,7 @@ def main():
 
     # ---- e2e: pinned host arrays through fq_replan_pairs_async, two contexts alternating
     host = []
-    for b in batches[:max(2, n_ctx)]:
+    for b in batches[:max(3, n_ctx)]:
         hw = dict(b.w)
         for k in PAIR_KEYS:
             hw[k] = torch.from_numpy(np.ascontiguousarray(b.w[k])).pin_memory().numpy()
@@ -405,7 +405,7 @@ def main():
                   feasible_whole=torch.zeros(nc, dtype=torch.uint8).pin_memory().numpy(), cost_whole=torch.zeros(nc, dtype=torch.float64).pin_memory().numpy(),
                   feasible_safe=torch.zeros(nc, dtype=torch.uint8).pin_memory().numpy(), cost_safe=torch.zeros(nc, dtype=torch.float64).pin_memory().numpy())
         host.append((hw, ho))
-    e2e_solvers = [capi.Solver(local) for _ in range(2)]     # plain contexts: the e2e leg measures the host path of one GPU
+    e2e_solvers = [capi.Solver(local) for _ in range(max(2, n_ctx))]     # plain contexts: the e2e leg measures the host path of one GPU
     if args.no_memo:
         for sv in e2e_solvers:
             sv.set_option("cert_memo", 0)
@@ -413,7 +413,7 @@ def main():
     def e2e_passes(n_pass):
         for p in range(n_pass):
             hw, ho = host[p % len(host)]
-            e2e_solvers[p % 2].replan_pairs(hw, deferred=True, out=ho)
+            e2e_solvers[p % len(e2e_solvers)].replan_pairs(hw, deferred=True, out=ho)
         for sv in e2e_solvers:
             sv.wait()
     e2e_inner = max(2, inner // 4)
@@ -458,7 +458,7 @@ def main():
                 "ms_per_pass": total_ms / args.steps / inner,
                 "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d * e2e_inner, "d2h_bytes_per_step": d2h * e2e_inner,
                         "passes_per_step": e2e_inner, "h2d_bytes_per_pass": h2d, "d2h_bytes_per_pass": d2h,
-                        "how": "fq_replan_pairs_async on two solver contexts + fq_wait; pinned host arrays; per-candidate flags and costs of both sweeps and the result records come back",
+                        "how": "fq_replan_pairs_async on %d solver contexts + fq_wait; pinned host arrays; per-candidate flags and costs of both sweeps and the result records come back" % len(e2e_solvers),
                         "matches_resident": same},
                 "gpu_launches": 11 * inner * args.steps,
                 "gpu_launches_note": "per pass: 2 dt-base, 2 grid-expand, 2 sweep solves, 2 selections, 1 winners' solve, R sampling, result records",

@@ -632,6 +632,19 @@ def test_wrong_polytope_size_hint_is_refused_not_overrun(solver):
     solver.set_option("max_faces_per_polytope", 0)
     assert not res[2][0].any() and (res[2][1] == -2).all()
     assert res[int(np.diff(fo).max())][0].any()
+    # the other hint, max_faces_per_prob (sizes the staged copy of the problem's rows), too small: the rows are not staged
+    # at all and every candidate of the problem is "not solved" with iters = -2, for both kernels
+    for generic in (0, 1):
+        solver.set_option("force_generic_kernel", generic)
+        feas = torch.ones(16, dtype=torch.uint8, device=dev)
+        cost = torch.zeros(16, dtype=torch.float64, device=dev)
+        iters = torch.zeros(16, dtype=torch.int32, device=dev)
+        solver.solve_multi_dev(10, True, 1, d["x0"].data_ptr(), d["xf"].data_ptr(), d["lim"].data_ptr(), d["po"].data_ptr(),
+                               d["fo"].data_ptr(), d["Ab"].data_ptr(), d["co"].data_ptr(), 16, int(fo[-1]) - 3, d["dt"].data_ptr(),
+                               d["sg"].data_ptr(), feas.data_ptr(), cost.data_ptr(), 0, iters.data_ptr())
+        torch.cuda.synchronize()
+        assert not feas.cpu().numpy().any() and (iters.cpu().numpy() == -2).all() and np.isinf(cost.cpu().numpy()).all()
+    solver.set_option("force_generic_kernel", 0)
 
 
 @pytest.mark.gpu
