@@ -275,7 +275,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* TZ, const d
         for (int j = lane; j < k; j += 32) m.r[j] = fma(-m.R[j * ld + k], rk, m.r[j]);
         __syncwarp();
       }
-      const bool dep = zz <= fmax(FQ_EPS_DEP * gg, FQ_ZZ_FLOOR);
+      const bool dep = zz <= fmax(FQ_EPS_DEP * gg, FQ_ZZ_FLOOR) || q >= nw;   // a full active set: nothing more fits
       // dual ratio test
       double best = INFINITY;
       int bk = -1;

@@ -627,7 +627,9 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
       const double t1 = warp_min(best);
       const double zzs = fmax(zz, 1e-300);
       const double rn = fast_rsqrt(zzs), rzz = fast_rcp(zzs);
-      const bool dep = zz <= fmax(FQ_EPS_DEP * gg, FQ_ZZ_FLOOR);
+      // q == NW: the active normals already span the space; whatever rounding leaves in z, the row is dependent (and a
+      // further column would not fit the factorisation's storage)
+      const bool dep = zz <= fmax(FQ_EPS_DEP * gg, FQ_ZZ_FLOOR) || q >= NW;
       int l = -1;
       if (t1 < INFINITY)
       {

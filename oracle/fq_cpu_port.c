@@ -332,7 +332,7 @@ static int solve_one(const plan_t* p, work_t* k, const double* x0, const double*
         for (int j = c + 1; j < q; j++) s -= k->R[j][c] * k->r[j];
         k->r[c] = s / k->R[c][c];
       }
-      const int dep = zz <= fmax(EPS_DEP * gg, ZZ_FLOOR);
+      const int dep = zz <= fmax(EPS_DEP * gg, ZZ_FLOOR) || q >= nw;
       double t1 = INFINITY;
       int l = -1;
       for (int c = 0; c < q; c++)
