@@ -684,3 +684,33 @@ def test_certificate_memo_changes_nothing_but_the_work(solver, oracle, N, P, ff)
     assert hits.sum() > 0, (hits.sum(), (f0 == 0).sum())
     fo, _ = oracle.solve_multi(*args, 8)
     assert np.array_equal(fo, f1)
+
+
+@pytest.mark.gpu
+def test_full_active_set_is_handled(solver, oracle):
+    """N = 15, free final position: 39 unknowns, and many infeasible candidates are only refuted once the active set holds
+    39 rows.  With a full active set every further row is dependent by definition; the solver must say so whatever
+    rounding leaves in the projection (round 2: a corridor of this family made the active set grow past its storage --
+    found by tools/stress_shapes.py under compute-sanitizer, fixed by the q >= NW guard).  Same corridors as that run."""
+    import math
+    N, ff, P = 15, False, 8
+    rng = np.random.default_rng(N * 1000 + P * 10 + int(ff))
+    mono = cr.sample_monotone_sigmas(N, P, 256, rng)
+    deep = 0
+    for c in range(4):
+        pb = cr.make_corridor(50000 + 97 * N + c, P, N, "uav", ff)
+        dti = capi.dt_initial(pb["x0"], pb["xf"], pb["lim"], N)
+        sig = np.vstack([mono[rng.choice(len(mono), 40, replace=False)], rng.integers(0, P, size=(24, N)).astype(np.uint8)])
+        dts = np.repeat(np.array([1.0, 1.5, 2.0, 3.0, 5.0, 8.0]) * max(dti, 2 * pb["DC"]), len(sig))
+        sigs = np.tile(sig, (6, 1))
+        fo, co, _ = oracle.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff, False, threads=8)
+        for generic in (0, 1):
+            solver.set_option("force_generic_kernel", generic)
+            fg, cg, _, it = solver.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff, False, True)
+            assert np.array_equal(fg, fo)
+            assert (it >= 0).all()                              # no iteration-cap / numeric give-ups either
+            ok = fo.astype(bool)
+            assert (np.abs(cg[ok] - co[ok]) / np.abs(co[ok])).max() < REL
+            deep += int((it >= 39).sum())
+    solver.set_option("force_generic_kernel", 0)
+    assert deep > 0                                             # the family does reach a full active set
