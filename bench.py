@@ -508,7 +508,7 @@ def main():
                             "algorithmic_bytes_per_candidate": BYTES_PER_CAND[10],
                             "note": "HBM fraction is tiny by construction (SURVEY 8d: 195 B and ~4 k warp instructions per candidate); "
                                     "the nearest hardware limits are the shared-memory data pipe and issue slots: see ncu"}
-        line["roofline"].update(ncu_summary(kernel_ms))
+        line["roofline"].update(ncu_summary(kernel_ms, nc, float(line["clocks"].get("sm_mhz") or 0.0)))
     # ---- parity: a slice of batch 0 against the CPU restatement of the chain, and the tolerance / margin picture
     if rank == 0 and not args.no_cpu_baseline:
         line["parity"] = parity_block(batches[0], res0, e2e_solvers[0], torch, capi, dev)
@@ -562,7 +562,7 @@ def main():
         dist.destroy_process_group()
 
 
-def ncu_summary(kernel_ms):
+def ncu_summary(kernel_ms, n_cand=0, sm_mhz=0.0):
     """DRAM traffic and pipe utilisation come from the committed ncu capture of this kernel (profiles/): they cannot be
     measured inside an unprofiled run."""
     try:
@@ -573,6 +573,14 @@ def ncu_summary(kernel_ms):
                        "issue_active_pct": float(np.mean([l["issue_active_pct"] for l in ls]))}}
         if all("lsu_data_pipe_pct_of_peak" in l for l in ls):
             out["ncu"]["shared_memory_pipe_pct_of_peak"] = float(np.mean([l["lsu_data_pipe_pct_of_peak"] for l in ls]))
+        if all("fp64_flop" in l for l in ls) and n_cand and sm_mhz:
+            # SURVEY 8(d)'s second roofline: fp64 flops the kernel executes (ncu's thread-level DFMA x2 + DADD + DMUL of
+            # the same launches, per candidate) x the live candidate rate, against the DFMA peak at the live SM clock
+            per_cand = float(np.mean([l["fp64_flop"] for l in ls])) / 65536.0
+            peak = float(ls[0]["fp64_peak_flop_per_cycle"]) * sm_mhz * 1e6 / 1e12
+            ach = per_cand * n_cand / (kernel_ms * 1e-3) / 1e12
+            out["fp64"] = {"flop_per_candidate": per_cand, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                           "peak_source": "ncu DFMA peak_sustained (%d flop/cycle over the chip) x SM clock under load" % int(ls[0]["fp64_peak_flop_per_cycle"])}
         return out
     except Exception:
         return {}

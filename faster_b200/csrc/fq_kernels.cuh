@@ -27,6 +27,11 @@
 #define FQ_SPLIT_ROWS 0       // 1: staged polytope rows as two arrays of 16-byte halves ([Ax Ay] and [Az b+tol]): both loads of
                               // the row scan become bank-conflict free (rows 32 bytes apart give a two-way conflict)
 #endif
+#ifndef FQ_CONST_PRECHECK
+#define FQ_CONST_PRECHECK 1   // 1: before anything else is set up, test the three control points of segment 0 that x0 and dt fix
+                              // (cp0, cp1, cp2: their plan rows are zero) against the faces of sigma[0]; a violated one
+                              // refutes the candidate (what the solve would find in its first iteration, same arithmetic)
+#endif
 #ifndef FQ_SCAN_UNROLL
 #define FQ_SCAN_UNROLL 1       // unroll factor of the corridor-row scan (more loads in flight per warp)
 #endif

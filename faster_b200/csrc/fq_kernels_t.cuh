@@ -812,6 +812,43 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
       }
     }
 #endif
+#if FQ_CONST_PRECHECK
+    // ---- control points 0..2 of segment 0 depend on x0 and dt only (rows 0, 4N+1, 5N+1 of the plan are zero, SY = 1e15):
+    //      one outside a face of sigma[0] refutes the candidate.  Same expression and rank key as the scan of gi_loop,
+    //      which would pick such a row first (SY outranks everything) and stop on it: flags are unchanged, iters = 1.
+    {
+      constexpr int YS[3] = { 0, 4 * N + 1, 5 * N + 1 };
+      if (SY[YS[0]] == 1e15 && SY[YS[1]] == 1e15 && SY[YS[2]] == 1e15)
+      {
+        double c[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int ax = 0; ax < 3; ax++) c[k][ax] = __shfl_sync(FULL, Yeq[YS[k] >> 5][ax], YS[k] & 31);
+        const int p0 = __shfl_sync(FULL, p, 0);
+        bool out = false;
+        for (int gf = sfo[p0] + lane; gf < sfo[p0 + 1]; gf += 32)
+        {
+          const double2 a01 = row_a01(sAb, gf, m.half_ofs), a23 = row_a23(sAb, gf, m.half_ofs);
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            out = out || rank_key(fma(a01.x, c[k][0], fma(a01.y, c[k][1], fma(a23.x, c[k][2], -a23.y))) * 1e15) > 0;
+        }
+        if (__any_sync(FULL, out))
+        {
+          if (lane == 0)
+          {
+            a.feasible[cand] = 0;
+            a.cost[cand] = INFINITY;
+            if (a.iters) a.iters[cand] = 1;
+          }
+          if (a.coeffs)
+            for (int idx = lane; idx < 12 * N; idx += 32) a.coeffs[(size_t)cand * N * 12 + idx] = 0.0;
+          return;
+        }
+      }
+    }
+#endif
     total_rows = build_items<D>(m, sfo, seg_ofs, lane, N, p, a.item_cap);
     if (total_rows < 0)
     { // the row list does not fit: report "not solved" (iters = -2 marks the cause)

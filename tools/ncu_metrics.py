@@ -42,6 +42,15 @@ for r in body:
         "sm_cycles_active_avg": val(r, "sm__cycles_active.avg"),
         "sm_cycles_active_max": val(r, "sm__cycles_active.max"),
     })
+    # fp64 work actually executed: thread-level DFMA (2 flop), DADD, DMUL per elapsed SM cycle (summed over the SMSPs) x cycles
+    try:
+        cyc = val(r, "sm__cycles_elapsed.avg")
+        per = {k: val(r, "smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % k) for k in ("dfma", "dadd", "dmul")}
+        launches[-1]["fp64_flop"] = (2.0 * per["dfma"] + per["dadd"] + per["dmul"]) * cyc
+        launches[-1]["fp64_thread_inst"] = {k: v * cyc for k, v in per.items()}
+        launches[-1]["fp64_peak_flop_per_cycle"] = 2.0 * val(r, "sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained")
+    except (KeyError, ValueError):
+        pass
 json.dump({"label": label, "report": rep, "note": "values under ncu replay (cold cache, serialised); per launch",
            "launches": launches}, open(out, "w"), indent=1)
 print(json.dumps(launches, indent=1))
