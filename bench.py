@@ -122,6 +122,7 @@ def make_single(cfg, n_corr, dt_initial):
 
 
 N_DT, N_SIG, CAND = 16, 64, 1024
+STRONG_CONTEXTS = 6      # chains in flight per GPU for the strong-scaling leg (small shards)
 
 
 def make_workload(n_corr, seed0, kind):
@@ -346,27 +347,28 @@ def main():
                for b in range(ring)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     ev_fork = torch.cuda.Event()
-    ev_join = [torch.cuda.Event() for _ in range(n_ctx)]
+    ev_join = [torch.cuda.Event() for _ in range(max(n_ctx, STRONG_CONTEXTS))]
 
-    def run_passes(n_pass, bl):
+    def run_passes(n_pass, bl, sv=None, st=None):
+        sv, st = sv or solvers, st or streams
         ev_fork.record(tstream)
-        for s in streams:
+        for s in st:
             s.wait_event(ev_fork)
         for p in range(n_pass):
-            k = p % n_ctx
+            k = p % len(sv)
             b = bl[p % len(bl)]
-            solvers[k].replan_pairs_dev(b.args, b.gathered.data_ptr() if b.gathered is not None else 0, streams[k].cuda_stream)
-        for k, s in enumerate(streams):
+            sv[k].replan_pairs_dev(b.args, b.gathered.data_ptr() if b.gathered is not None else 0, st[k].cuda_stream)
+        for k, s in enumerate(st):
             ev_join[k].record(s)
             tstream.wait_event(ev_join[k])
 
-    def timed(n_steps, n_pass, bl):
+    def timed(n_steps, n_pass, bl, sv=None, st=None):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
         barrier()
         for i in range(n_steps):
             flush.zero_()                                    # L2 flush between timed steps (outside the events)
             ev[i][0].record(tstream)
-            run_passes(n_pass, bl)
+            run_passes(n_pass, bl, sv, st)
             ev[i][1].record(tstream)
         barrier()
         return [a.elapsed_time(b) for a, b in ev]
@@ -384,14 +386,26 @@ def main():
     strong = None
     if world > 1:
         lo, hi = capi.shard_range(C, None, rank, world)
-        sb = [PairBatch(load_cfg4((b * C + lo) % n_fix, hi - lo), dev, torch, capi, gather_world=world) for b in range(ring)]
+        # a shard of 8-32 corridors does not fill the GPU: more chains in flight (measured on one GPU, 8 corridors per pass:
+        # 21 / 49 / 58 M pairs/s with 1 / 3 / 6 contexts; profiles/r02p_contexts.log), each with its own communicator
+        n_s = n_ctx if args.single_stream else max(n_ctx, STRONG_CONTEXTS)
+        sv_s, st_s = list(solvers), list(streams)
+        for k in range(n_ctx, n_s):
+            sv = capi.Solver(local)
+            uid = [capi.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            sv.comm_init(uid[0], rank, world)
+            sv_s.append(sv)
+            st_s.append(torch.cuda.Stream(device=dev))
+        ring_s = ((ring + n_s - 1) // n_s) * n_s
+        sb = [PairBatch(load_cfg4((b * C + lo) % n_fix, hi - lo), dev, torch, capi, gather_world=world) for b in range(ring_s)]
         # equal shard sizes are what the all-gather needs: C is a multiple of the world sizes used (64 / 2,4,8)
-        run_passes(inner, sb)
-        sms = timed(max(3, args.steps // 2), inner, sb)
+        run_passes(inner, sb, sv_s, st_s)
+        sms = timed(max(3, args.steps // 2), inner, sb, sv_s, st_s)
         t = torch.tensor([float(sum(sms))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         strong = {"scaling": "strong", "value": C * 1024 * inner * len(sms) / (float(t.item()) * 1e-3), "unit": "pairs/s",
-                  "pairs_per_pass_total": C * 1024, "corridors_per_gpu_per_pass": hi - lo, "steps": len(sms)}
+                  "pairs_per_pass_total": C * 1024, "corridors_per_gpu_per_pass": hi - lo, "steps": len(sms), "contexts": n_s}
         del sb
 
     # ---- e2e: pinned host arrays through fq_replan_pairs_async, two contexts alternating
