@@ -726,16 +726,20 @@ def latency_block(solver, capi):
         for _ in range(n):
             t0 = time.perf_counter(); r = fn(); lat.append(time.perf_counter() - t0)
         return float(np.median(lat[skip:]) * 1e6), r
-    us, g = med(lambda: solver.gen_new_traj(N_SEG, x0, xf, lim, polys, dts10, sig66, True))
-    us_x, ge = med(lambda: solver.gen_new_traj_exact(N_SEG, x0, xf, lim, polys, dts10, True), 40)
+    def med2(fn, n=50, skip=10):
+        """the same call with the early exit off / on, ALTERNATING (clock ramps and host noise hit both alike)"""
+        lat = ([], [])
+        r = [None, None]
+        for i in range(2 * n):
+            solver.set_option("sweep_early_exit", i & 1)
+            t0 = time.perf_counter(); r[i & 1] = fn(); lat[i & 1].append(time.perf_counter() - t0)
+        solver.set_option("sweep_early_exit", 0)
+        return float(np.median(lat[0][skip:]) * 1e6), r[0], float(np.median(lat[1][skip:]) * 1e6), r[1]
     w1 = load_cfg4(0, 1)
-    us_pair, rp = med(lambda: solver.replan_pairs(w1, want_candidates=False), 40)
-    # what the drop-in class does (include/solverGurobi.hpp switches the early exit on: only the winner is needed)
-    solver.set_option("sweep_early_exit", 1)
-    us_ee, g_ee = med(lambda: solver.gen_new_traj(N_SEG, x0, xf, lim, polys, dts10, sig66, True))
-    us_x_ee, ge_ee = med(lambda: solver.gen_new_traj_exact(N_SEG, x0, xf, lim, polys, dts10, True), 40)
-    us_pair_ee, rp_ee = med(lambda: solver.replan_pairs(w1, want_candidates=False), 40)
-    solver.set_option("sweep_early_exit", 0)
+    # early exit = what the drop-in class does (include/solverGurobi.hpp switches it on: only the winner is needed)
+    us, g, us_ee, g_ee = med2(lambda: solver.gen_new_traj(N_SEG, x0, xf, lim, polys, dts10, sig66, True))
+    us_x, ge, us_x_ee, ge_ee = med2(lambda: solver.gen_new_traj_exact(N_SEG, x0, xf, lim, polys, dts10, True), 40)
+    us_pair, rp, us_pair_ee, rp_ee = med2(lambda: solver.replan_pairs(w1, want_candidates=False), 40)
     import itertools
     pb6 = cr.make_corridor(10000, 3, 6)
     sig729 = np.array(list(itertools.product(range(3), repeat=6)), np.uint8)

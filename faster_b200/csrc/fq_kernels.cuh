@@ -32,6 +32,9 @@
                               // (cp0, cp1, cp2: their plan rows are zero) against the faces of sigma[0]; a violated one
                               // refutes the candidate (what the solve would find in its first iteration, same arithmetic)
 #endif
+#ifndef FQ_EE_CAP_ALWAYS
+#define FQ_EE_CAP_ALWAYS 0     // 1: cap the grid of an early-exit sweep even when the whole sweep fits the GPU at once (tuning)
+#endif
 #ifndef FQ_SCAN_UNROLL
 #define FQ_SCAN_UNROLL 1       // unroll factor of the corridor-row scan (more loads in flight per warp)
 #endif

@@ -1250,12 +1250,15 @@ cudaError_t launch_t(const FqKernelArgs& a, long long total_cand_hint, cudaStrea
     cc.per_sm = q < 1 ? 1 : q;
     cc.smem_occ = smem;
   }
-  long long grid = (long long)cc.per_sm * sm_count;
+  const long long resident = (long long)cc.per_sm * sm_count;
+  long long grid = resident;
   const long long need = (total_cand_hint + W - 1) / W;      // no point in more CTAs than candidates / warps
   if (grid > need) grid = need;
-  if (a.first_feasible && a.sorted_dt && a.ee_width > 0)
-  { // early exit on an ascending sweep: keep only ~two time allocations per problem in flight, so that the larger ones --
-    // which cannot win once a smaller one is feasible, and hold the long solves -- are mostly never started
+  if (a.first_feasible && a.sorted_dt && a.ee_width > 0 && (FQ_EE_CAP_ALWAYS || need > resident))
+  { // early exit on an ascending sweep that does not fit the GPU at once: keep only ~two time allocations per problem in
+    // flight, so that the larger ones -- which cannot win once a smaller one is feasible -- are mostly never started.
+    // A sweep that fits (one genNewTraj: a few hundred candidates) starts everything: a cap would only serialise it
+    // (measured on a cfg4 corridor whose first two factors are infeasible: 105 us capped, 91 us not).
     const long long cap = ((long long)a.n_prob * 2 * a.ee_width + W - 1) / W;
     if (grid > cap) grid = cap;
   }
