@@ -789,6 +789,7 @@ def bench_single(args, name, torch, capi, dev, local, world, rank, barrier, main
                                w["cand"], w["max_faces"], d["dt"].data_ptr(), d["sigma"].data_ptr(), feas.data_ptr(), cost.data_ptr(), 0,
                                its.data_ptr() if with_iters else 0, st.cuda_stream)
     per_launch_ms = None
+    torch.cuda.synchronize()                             # the arrays above were filled on the previous current stream
     for _ in range(3):
         launch()
     torch.cuda.synchronize()

@@ -116,6 +116,7 @@ def test_pairs_device_pointer_entry(solver):
     gathered = torch.zeros(n * 144, dtype=torch.uint8, device=dev)
     a = capi.pair_args(w, lambda k: d[k].data_ptr(), {k: v.data_ptr() for k, v in out.items()})
     st = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()        # the fills above run on torch's stream
     solver.replan_pairs_dev(a, gathered.data_ptr(), st.cuda_stream)
     solver.replan_pairs_dev(a, gathered.data_ptr(), st.cuda_stream)       # back to back on one stream: ordered
     st.synchronize()

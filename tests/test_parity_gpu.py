@@ -299,6 +299,7 @@ def test_device_pointer_entry_matches_host_entry(solver):
     cost = torch.zeros(n, dtype=torch.float64, device=dev)
     coef = torch.zeros(n * N * 12, dtype=torch.float64, device=dev)
     st = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()        # the fills above run on torch's stream; the library launches on `st`
     with torch.cuda.stream(st):
         solver.solve_multi_dev(N, False, len(probs), d["x0"].data_ptr(), d["xf"].data_ptr(), d["lim"].data_ptr(),
                                d["poly_ofs"].data_ptr(), d["face_ofs"].data_ptr(), d["Ab"].data_ptr(),
@@ -454,6 +455,7 @@ def test_non_finite_inputs_are_rejected_or_survive(solver):
                      co=t(np.array([0, 8], np.int32)), dt=t(dts), sg=t(sig))
             feas = torch.ones(8, dtype=torch.uint8, device=dev)
             cost = torch.zeros(8, dtype=torch.float64, device=dev)
+            torch.cuda.synchronize()    # torch's fills run on its own stream, the library on the context's
             solver.solve_multi_dev(10, True, 1, d["x0"].data_ptr(), d["xf"].data_ptr(), d["lim"].data_ptr(),
                                    d["po"].data_ptr(), d["fo"].data_ptr(), d["Ab"].data_ptr(), d["co"].data_ptr(), 8,
                                    int(fo[-1]), d["dt"].data_ptr(), d["sg"].data_ptr(), feas.data_ptr(), cost.data_ptr())
@@ -624,6 +626,7 @@ def test_wrong_polytope_size_hint_is_refused_not_overrun(solver):
         feas = torch.ones(16, dtype=torch.uint8, device=dev)
         cost = torch.zeros(16, dtype=torch.float64, device=dev)
         iters = torch.zeros(16, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()        # torch's fills run on its own stream, the library on the context's (found by racecheck's timing)
         solver.solve_multi_dev(10, True, 1, d["x0"].data_ptr(), d["xf"].data_ptr(), d["lim"].data_ptr(), d["po"].data_ptr(),
                                d["fo"].data_ptr(), d["Ab"].data_ptr(), d["co"].data_ptr(), 16, int(fo[-1]), d["dt"].data_ptr(),
                                d["sg"].data_ptr(), feas.data_ptr(), cost.data_ptr(), 0, iters.data_ptr())
@@ -639,6 +642,7 @@ def test_wrong_polytope_size_hint_is_refused_not_overrun(solver):
         feas = torch.ones(16, dtype=torch.uint8, device=dev)
         cost = torch.zeros(16, dtype=torch.float64, device=dev)
         iters = torch.zeros(16, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()        # torch's fills run on its own stream, the library on the context's (found by racecheck's timing)
         solver.solve_multi_dev(10, True, 1, d["x0"].data_ptr(), d["xf"].data_ptr(), d["lim"].data_ptr(), d["po"].data_ptr(),
                                d["fo"].data_ptr(), d["Ab"].data_ptr(), d["co"].data_ptr(), 16, int(fo[-1]) - 3, d["dt"].data_ptr(),
                                d["sg"].data_ptr(), feas.data_ptr(), cost.data_ptr(), 0, iters.data_ptr())

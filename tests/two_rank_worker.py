@@ -39,6 +39,7 @@ def main():
     res = torch.zeros(n * 144, dtype=torch.uint8, device=dev)
     allres = torch.zeros(world * n * 144, dtype=torch.uint8, device=dev)
     a = capi.pair_args(w, lambda k: d[k].data_ptr(), {"results": res.data_ptr()})
+    torch.cuda.synchronize()        # the fills above run on torch's stream, the library on the context's
     s.replan_pairs_dev(a, allres.data_ptr(), 0)
     s.wait()
     np.save(out_path, np.frombuffer(allres.cpu().numpy().tobytes(), capi.PAIR_RESULT_DTYPE))

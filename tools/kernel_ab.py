@@ -37,6 +37,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
                                    b.d["poly_ofs_" + kind].data_ptr(), b.d["face_ofs_" + kind].data_ptr(), b.d["Ab_" + kind].data_ptr(),
                                    d["cand_ofs"].data_ptr(), nc // b.w["n_prob"], b.w["max_faces_" + kind], d["dt"].data_ptr(),
                                    d["sigma"].data_ptr(), feas.data_ptr(), cost.data_ptr(), 0, its.data_ptr() if wi else 0, st.cuda_stream)
+        torch.cuda.synchronize()
         launch(False)
         ms = []
         for _ in range(20):
