@@ -4,7 +4,12 @@
   (2) for candidates the GPU reports infeasible, the Farkas certificate the solver stopped on (fq_solve_batch_cert) is
       checked on those literal rows: multipliers y >= 0 on the inequality rows, free multipliers on the equality rows
       (initial state, final state, continuity), combination of the rows = 0, combination of the right-hand sides < 0.
-      Such a certificate proves infeasibility whatever solver produced it.
+      Such a certificate proves infeasibility whatever solver produced it;
+  (3) for candidates the GPU reports solved, an OPTIMALITY proof on the same literal rows (oracle/proofs.py): the GPU's
+      coefficients satisfy every row, and Karush-Kuhn-Tucker multipliers exist for them (free on the equality rows, >= 0 on
+      the tight inequality rows, stationarity residual at rounding level).  For this convex QP that is sufficient: the point
+      is the optimum of the reference's model and the reported cost is its minimum -- again whatever solver produced it.
+      The prover's own negative controls run on the CPU (tests/test_proofs_cpu.py).
 """
 import numpy as np
 import pytest
@@ -61,31 +66,9 @@ def test_cuda_path_against_highs_on_the_literal_model(solver, name, N, P, ff, pr
     assert checked == 90 and feas_seen > 10 and infeas_seen > 5 and highs_agree > 5
 
 
-def _literal_row_index(N, polys, sigma):
-    """Row numbers of oracle/model_fullspace.build's inequality block for the certificate's row ids."""
-    face_ofs = np.concatenate([[0], np.cumsum([len(b) for _, b in polys])]).astype(int)
-    box = {}
-    r = 0
-    for t in range(N):
-        for ax in range(3):
-            for typ in range(3):
-                box[(typ, ax, t, 1)] = r
-                box[(typ, ax, t, 0)] = r + 1
-                r += 2
-    cor = {}
-    for t in range(N):
-        p = int(sigma[t])
-        F = len(polys[p][1])
-        for k in range(4):
-            for f in range(F):
-                cor[(t, face_ofs[p] + f, k)] = r
-                r += 1
-    return box, cor, r
-
-
 @pytest.mark.parametrize("name,N,P,ff,profile", CASES)
 def test_infeasibility_certificates_hold_on_the_literal_rows(solver, name, N, P, ff, profile):
-    from oracle import model_fullspace as mf
+    from oracle import model_fullspace as mf, proofs
     rng = np.random.default_rng(7 + N + P)
     verified = 0
     for seed in (6200, 6201, 6202, 6203):
@@ -94,29 +77,29 @@ def test_infeasibility_certificates_hold_on_the_literal_rows(solver, name, N, P,
         f2, _, _, _ = solver.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff)
         assert np.array_equal(fg, f2)                          # generic (certifying) and specialised kernel agree
         for i in np.flatnonzero(fg == 0)[:12]:
-            n = int(cert[i, 0])
-            assert n >= 1, "infeasible candidate without certificate"
-            Q, Aeq, beq, Ain, bin_ = mf.build(N, pb["x0"], pb["xf"], pb["lim"], dts[i], pb["polys"], sigs[i], ff)
-            box, cor, n_rows = _literal_row_index(N, pb["polys"], sigs[i])
-            assert n_rows == len(bin_)
-            y = np.zeros(len(bin_))
-            for k in range(n):
-                rid, mult = int(round(cert[i, 2 + 2 * k])), cert[i, 3 + 2 * k]
-                assert mult >= -1e-12
-                if rid >= 10000000:
-                    rid -= 10000000
-                    typ, rem = divmod(rid, 10000); ax, rem = divmod(rem, 1000); t, s = divmod(rem, 10)
-                    y[box[(typ, ax, t, s)]] += mult
-                else:
-                    t, rem = divmod(rid, 100000); f, kcp = divmod(rem, 10)
-                    y[cor[(t, f, kcp)]] += mult
-            g = Ain.T @ y                                      # must vanish modulo the equality rows
-            mu, *_ = np.linalg.lstsq(Aeq.T, -g, rcond=None)
-            resid = np.abs(g + Aeq.T @ mu).max()
-            scale = max(1.0, np.abs(g).max())
-            assert resid <= 1e-7 * scale, (name, seed, i, resid, scale)
-            gap = float(bin_ @ y + beq @ mu)                   # < 0: the rows cannot hold together
-            assert gap < -1e-9, (name, seed, i, gap)
-            assert abs(gap + cert[i, 1]) <= 1e-6 * max(1.0, abs(gap)), (gap, cert[i, 1])   # = minus the violation the solver saw
+            model = mf.build(N, pb["x0"], pb["xf"], pb["lim"], dts[i], pb["polys"], sigs[i], ff)
+            proofs.assert_infeasible(model, N, pb["polys"], sigs[i], cert[i])
             verified += 1
     assert verified >= 10
+
+
+@pytest.mark.parametrize("name,N,P,ff,profile", CASES)
+def test_solved_flags_carry_optimality_proofs(solver, name, N, P, ff, profile):
+    """Every candidate the product kernel reports solved: its coefficients are feasible on the literal rows AND carry KKT
+    multipliers there (stationarity residual <= 1e-6 relative, complementarity gap <= 1e-7 relative), the reported cost is
+    the cost of that point.  Together with the Farkas test above every flag of these batches is proved, not compared."""
+    from oracle import model_fullspace as mf, proofs
+    rng = np.random.default_rng(11 + N + P)
+    proved = active = 0
+    worst = 0.0
+    for seed in (6400, 6401, 6402):
+        pb, dts, sigs = _candidates(N, P, ff, profile, seed, 8, rng)
+        fg, cg, cog, _ = solver.solve_batch(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], dts, sigs, ff, want_coeffs=True)
+        for i in np.flatnonzero(fg):
+            model = mf.build(N, pb["x0"], pb["xf"], pb["lim"], dts[i], pb["polys"], sigs[i], ff)
+            r = proofs.assert_optimal(model, cog[i], cg[i])
+            proved += 1
+            active += r["n_active"] > 0
+            worst = max(worst, r["resid"])
+    assert proved >= 20 and active >= 5, (proved, active)
+    print("%s: %d optima proved on the literal model, %d with tight rows, worst stationarity residual %.1e" % (name, proved, active, worst))
