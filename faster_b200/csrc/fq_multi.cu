@@ -269,6 +269,16 @@ int fq_replan_pairs_sharded(fq_ctx* g, const fq_pair_args* a, bool deferred)
 {
   fq_ctx* ctx = g;
   if (!a || a->n_prob <= 0 || !a->results) return fq_fail(g, FQ_E_ARG, "bad arguments");
+  // the shards' corridor descriptions are rebased on the host before the per-member validation runs: the arrays read
+  // here must exist (everything else is checked by the member's own call)
+  if (!a->x0 || !a->xf_whole || !a->xf_safe || !a->lim || !a->poly_ofs_whole || !a->face_ofs_whole || !a->poly_ofs_safe ||
+      !a->face_ofs_safe)
+    return fq_fail(g, FQ_E_ARG, "NULL argument");
+  if (a->n_fac_whole <= 0 || a->n_fac_safe <= 0 || a->n_sig_whole <= 0 || a->n_sig_safe <= 0)
+    return fq_fail(g, FQ_E_ARG, "empty factor / assignment grid");
+  for (int j = 0; j < a->n_prob; j++)
+    if (a->poly_ofs_whole[j + 1] < a->poly_ofs_whole[j] || a->poly_ofs_safe[j + 1] < a->poly_ofs_safe[j])
+      return fq_fail(g, FQ_E_ARG, "poly_ofs not monotone");
   const int P = a->n_prob, world = g->world;
   const bool group = g->is_group;
   const int n_local = group ? world : 1;
@@ -350,6 +360,8 @@ extern "C" int fq_solve_multi_sharded(fq_ctx* g, int N, int force_final, int n_p
   if (n_prob <= 0 || !x0 || !xf || !lim || !poly_ofs || !face_ofs || !cand_ofs || !dt || !feasible || !cost || !win_idx || !win_cost)
     return fq_fail(g, FQ_E_ARG, "bad arguments");
   if (poly_ofs[0] != 0 || face_ofs[0] != 0 || cand_ofs[0] != 0) return fq_fail(g, FQ_E_ARG, "offset arrays must start at 0");
+  for (int j = 0; j < n_prob; j++)             // the shards are rebased on the host before the members validate theirs
+    if (poly_ofs[j + 1] < poly_ofs[j] || cand_ofs[j + 1] < cand_ofs[j]) return fq_fail(g, FQ_E_ARG, "offset arrays not monotone");
   const int world = g->world;
   const bool group = g->is_group;
   const int n_local = group ? world : 1;
