@@ -37,7 +37,8 @@ def prove_optimal(Q, Aeq, beq, Ain, bin_, z, active_tol=1e-7):
     lo = np.concatenate([np.full(Aeq.shape[0], -np.inf), np.zeros(len(act))])
     sol = lsq_linear(M / cs, -g, bounds=(lo, np.full(M.shape[1], np.inf)), method="bvls", tol=1e-14, max_iter=4000)
     x = sol.x / cs
-    mu, lam = x[:Aeq.shape[0]], x[Aeq.shape[0]:]
+    x[Aeq.shape[0]:] = np.maximum(x[Aeq.shape[0]:], 0.0)     # the certificate's multipliers are non-negative by construction
+    mu, lam = x[:Aeq.shape[0]], x[Aeq.shape[0]:]             # (the fit may leave -1e-17; the residual below is that of the clipped set)
     rho = g + M @ x
     return {
         "eq": float(np.abs(req).max()),

@@ -25,7 +25,7 @@ s = capi.Solver(0)
 rng = np.random.default_rng(20260923)
 res = {"corridors": 0, "candidates": 0, "solved_proved_optimal": 0, "not_solved_proved_infeasible": 0, "kernels_disagree": 0,
        "abandoned": 0, "worst_stationarity_resid": 0.0, "worst_gap": 0.0, "worst_row_excess": 0.0, "with_tight_rows": 0,
-       "by_kind": {}}
+       "proof_failures": 0, "first_failures": [], "by_kind": {}}
 t0 = time.time()
 
 
@@ -42,20 +42,29 @@ def prove_batch(kind, N, x0, xf, lim, polys, dts, sigs, ff):
     for i in range(len(dts)):
         model = mf.build(N, x0, xf, lim, dts[i], polys, sigs[i], ff)
         res["candidates"] += 1
-        if fg[i]:
-            r = proofs.assert_optimal(model, cog[i], cg[i])
-            res["solved_proved_optimal"] += 1
-            k["solved"] += 1
-            res["with_tight_rows"] += int(r["n_active"] > 0)
-            res["worst_stationarity_resid"] = max(res["worst_stationarity_resid"], r["resid"])
-            res["worst_gap"] = max(res["worst_gap"], r["gap"])
-            res["worst_row_excess"] = max(res["worst_row_excess"], r["eq"], r["ineq"])
-        elif int(cert[i, 0]) >= 1:
-            proofs.assert_infeasible(model, N, polys, sigs[i], cert[i])
-            res["not_solved_proved_infeasible"] += 1
-            k["not_solved"] += 1
-        else:
-            res["abandoned"] += 1                            # iteration cap / non-finite input: no verdict, no proof
+        try:
+            prove_one(kind, k, N, polys, sigs[i], model, fg[i], cg[i], cog[i], cert[i])
+        except AssertionError as e:                         # counted and shown, never swallowed: the run fails at the end
+            res["proof_failures"] += 1
+            if len(res["first_failures"]) < 5:
+                res["first_failures"].append("%s dt=%.6g sigma=%s flag=%d: %s" % (kind, dts[i], list(map(int, sigs[i])), fg[i], str(e)[:300]))
+
+
+def prove_one(kind, k, N, polys, sigma, model, flag, cost, coeffs, cert_row):
+    if flag:
+        r = proofs.assert_optimal(model, coeffs, cost)
+        res["solved_proved_optimal"] += 1
+        k["solved"] += 1
+        res["with_tight_rows"] += int(r["n_active"] > 0)
+        res["worst_stationarity_resid"] = max(res["worst_stationarity_resid"], r["resid"])
+        res["worst_gap"] = max(res["worst_gap"], r["gap"])
+        res["worst_row_excess"] = max(res["worst_row_excess"], r["eq"], r["ineq"])
+    elif int(cert_row[0]) >= 1:
+        proofs.assert_infeasible(model, N, polys, sigma, cert_row)
+        res["not_solved_proved_infeasible"] += 1
+        k["not_solved"] += 1
+    else:
+        res["abandoned"] += 1                                # iteration cap / non-finite input: no verdict, no proof
 
 
 w = bench.load_cfg4(0, n_corr)
@@ -80,5 +89,5 @@ for seed in range(5000, 5000 + max(2, n_corr // 8)):        # BASELINE config 5:
                 allm[rng.integers(0, len(allm), n_cand)], True)
     res["corridors"] += 1
 res["seconds"] = round(time.time() - t0, 1)
-assert res["kernels_disagree"] == 0
 print(json.dumps(res))
+assert res["kernels_disagree"] == 0 and res["proof_failures"] == 0
