@@ -10,11 +10,13 @@ ZZ_FLOOR = 1e-30
 MAX_ITERS = 400
 
 
-def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised=False, thin=False):
+def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised=False, thin=False, trace=None):
     """-> (status, cost, coeffs[N,12], iters).  normalised=False mirrors the size-generic kernel (entering row = largest
     violation); normalised=True mirrors the size-specialised kernel (largest (violation - tol) / |TZ[y]|).
     thin=True: the thin factorisation of the specialised kernel (J1 = orthonormal basis of the active normals only,
-    Gram-Schmidt with one re-orthogonalisation pass when the residual is small) instead of the full orthogonal J."""
+    Gram-Schmidt with one re-orthogonalisation pass when the residual is small) instead of the full orthogonal J.
+    trace: a list that receives, at every scan for the entering row, (w, length of the path w travelled since the previous
+    scan) -- tools/scan_skip_model.py studies how much of a scan a distance bound could skip."""
     TZ, T0, FT = tables
     ne = 3 if force_final else 2
     nz, NY = N - ne, 6 * N + 1
@@ -51,7 +53,11 @@ def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised
     def rank(viol, y, scale=1.0):
         return (viol - TOL) * SY[y] / scale if normalised else viol - TOL
 
+    travelled = 0.0
     while True:
+        if trace is not None:
+            trace.append((w.copy(), travelled))
+            travelled = 0.0
         best, desc = 0.0, None
         for typ in range(3):
             for ax in range(3):
@@ -107,6 +113,7 @@ def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised
                 break
             if t2 <= t1:
                 w = w + t2 * z
+                travelled += abs(t2) * np.sqrt(zz)
                 lam[:q] -= t2 * r
                 lam_p += t2
                 nrm = np.sqrt(zz)
@@ -130,6 +137,7 @@ def solve(tables, N, x0, xf, lim, dt, polys, sigma, force_final=True, normalised
                 break
             if not dep:
                 w = w + t1 * z
+                travelled += abs(t1) * np.sqrt(zz)
             lam[:q] -= t1 * r
             lam_p += t1
             # drop l
