@@ -38,6 +38,19 @@
 #ifndef FQ_SCAN_UNROLL
 #define FQ_SCAN_UNROLL 1       // unroll factor of the corridor-row scan (more loads in flight per warp)
 #endif
+#ifndef FQ_MIN_REDUX
+#define FQ_MIN_REDUX 1         // 1: the ratio test's warp minimum through two integer redux.sync on the order-preserving bit
+                               // pattern of the doubles (exact) instead of five dependent shuffle + min rounds.  Measured
+                               // (tools/kernel_ab.py, same box, 3 rounds): whole sweep 0.3976 -> 0.3825 ms, safe 0.5338 -> 0.5110 ms
+#endif
+#ifndef FQ_GI_HOIST
+#define FQ_GI_HOIST 0          // 1: the lane's (axis, column) of the entering row's normal computed once per candidate and the
+                               // per-iteration code branch-free.  Measured +0.8 % / +1.0 % SLOWER (two more live registers): off
+#endif
+#ifndef FQ_ITEMS_BY_SEGMENT
+#define FQ_ITEMS_BY_SEGMENT 0  // 1: the corridor item list written by two lanes per segment (even / odd faces) instead of one
+                               // lane per item with a four-step search for its segment.  Measured +3.2 % / +1.3 % SLOWER: off
+#endif
 #define FQ_EPS_DEP 1e-18      // squared sine below which a new normal counts as dependent on the active set
 #define FQ_ZZ_FLOOR 1e-30
 #define FQ_MAX_ITERS 400

@@ -80,9 +80,22 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 __device__ __forceinline__ double warp_min(double v)
 {
+#if FQ_MIN_REDUX
+  // order-preserving integer image of a double (no NaN here): for negative values the magnitude bits are inverted, so the
+  // signed order of the hi words and the unsigned order of the lo words are the numeric order; two redux.sync give the
+  // exact minimum
+  const int hi = __double2hiint(v), neg = hi >> 31;
+  const int khi = hi ^ (neg & 0x7fffffff);
+  const unsigned klo = (unsigned)__double2loint(v) ^ (unsigned)neg;
+  const int mh = __reduce_min_sync(FULL, khi);
+  const unsigned ml = __reduce_min_sync(FULL, khi == mh ? klo : 0xffffffffu);
+  const int mneg = mh >> 31;
+  return __hiloint2double(mh ^ (mneg & 0x7fffffff), (int)(ml ^ (unsigned)mneg));
+#else
 #pragma unroll
   for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
   return v;
+#endif
 }
 
 // staged polytope rows: row gf = (a01 = [Ax Ay], a23 = [Az b+tol]); interleaved (32-byte rows) or split into two arrays
@@ -362,6 +375,20 @@ __device__ __forceinline__ int build_items(const WarpState<D>& m, const int* __r
   }
   const int total_rows = __shfl_sync(FULL, incl, n_seg - 1);
   if (total_rows > item_cap) return -1;     // a wrong max_faces_per_polytope hint (device-pointer entry): refuse, never overrun
+#if FQ_ITEMS_BY_SEGMENT
+  { // lanes tl and tl + 16 write the items of segment tl (even / odd faces), same order as the list built item by item
+    (void)seg_ofs;
+    const int tl = lane & 15;
+    const int first = __shfl_sync(FULL, incl - F, tl);
+    const int meta = __shfl_sync(FULL, (need0 << 11) | sfo[lane < n_seg ? p : 0], tl);
+    const int Ft = __shfl_sync(FULL, F, tl);                 // 0 beyond the last segment
+    const int Fmax = __reduce_max_sync(FULL, F);
+    for (int f = lane >> 4; f < Fmax; f += 2)
+      if (f < Ft) m.items[first + f] = (unsigned short)((tl << 12) | (meta + f));
+    __syncwarp();
+    return total_rows;
+  }
+#endif
   // seg_ofs[t] = first item of segment t; seg_ofs[16 + t] = (need_cp0 << 11) | first staged face of sigma[t]
   if (lane < n_seg) { seg_ofs[lane] = incl - F; seg_ofs[16 + lane] = (need0 << 11) | sfo[p]; }
   else if (lane < 16) seg_ofs[lane] = 0x7fffffff;
@@ -401,6 +428,15 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
   int aseg[SLOTS];
 #pragma unroll
   for (int s = 0; s < SLOTS; s++) { r[s] = 0; z[s] = 0; dreg[s] = 0; aseg[s] = 0; }
+#if FQ_GI_HOIST
+  int gcol[SLOTS];                                    // variable j = lane + 32 s of w: axis << 8 | column of the plan table
+#pragma unroll
+  for (int s = 0; s < SLOTS; s++)
+  {
+    const int j = lane + 32 * s, ax = j / NZ;
+    gcol[s] = j < NW ? (ax << 8) | (j - ax * NZ) : (3 << 8);
+  }
+#endif
   int status = -2;
   while (status == -2)
   {
@@ -501,8 +537,14 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
           dreg[s] = fma(w0, s0[s], fma(w1, s1[s], w2 * s2[s]));
           if (j < q) m.d[j] = dreg[s];
           // this lane's component of g: variable j = (axis, column) of the plan table
+#if FQ_GI_HOIST
+          const int ax = gcol[s] >> 8;
+          const double wsel = ax == 0 ? w0 : (ax == 1 ? w1 : (ax == 2 ? w2 : 0.0));
+          gi[s] = wsel * TZ[y * D::TZLD + (gcol[s] & 0xff)];
+#else
           const int ax = j / NZ, kk = j - ax * NZ;
           gi[s] = j < NW ? (ax == 0 ? w0 : (ax == 1 ? w1 : w2)) * TZ[y * D::TZLD + kk] : 0.0;
+#endif
         }
       }
       __syncwarp();
@@ -921,7 +963,7 @@ __device__ void solve_candidate(const FqKernelArgs& a, const double* __restrict_
       const double u = m.Y[ax * NYP + 3 * N + 1 + t];
       cp = fma(u, u, cp);
     }
-  const double cost = warp_sum(cp) * (inv3 * inv3);
+  const double cost = status == 1 ? warp_sum(cp) * (inv3 * inv3) : INFINITY;   // (status is warp-uniform)
   if (lane == 0)
   {
     a.feasible[cand] = status == 1;
