@@ -51,6 +51,17 @@
 #define FQ_ITEMS_BY_SEGMENT 0  // 1: the corridor item list written by two lanes per segment (even / odd faces) instead of one
                                // lane per item with a four-step search for its segment.  Measured +3.2 % / +1.3 % SLOWER: off
 #endif
+#ifndef FQ_LAZY_LEAVING
+#define FQ_LAZY_LEAVING 0      // 1: the index of the blocking row (ballot + shuffle) is looked up only when a partial step is taken.
+                               // Measured (tools/kernel_ab.py, 3 rounds, profiles/r02aa_kernel_ab.log): no change (0.3862 / 0.5063 ms
+                               // against 0.3862 / 0.5069 ms): off
+#endif
+#ifndef FQ_SCAN_ARGMAX
+#define FQ_SCAN_ARGMAX 0       // 1: the scan remembers WHICH control point of the winning (segment, face) item ranked highest (two
+                               // bits of the code) instead of re-evaluating the item's four points when the entering row is decoded:
+                               // same keys, same order, same choice.  Measured: whole 0.3861 (=), safe 0.5022 ms (-0.9 %); with
+                               // FQ_LAZY_LEAVING whole +0.3 %, safe -1.5 %: inside the noise of the A/B, left off
+#endif
 #define FQ_EPS_DEP 1e-18      // squared sine below which a new normal counts as dependent on the active set
 #define FQ_ZZ_FLOOR 1e-30
 #define FQ_MAX_ITERS 400

@@ -454,10 +454,24 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
       const double u1 = fma(a01.x, Y0[y1], fma(a01.y, Y1[y1], fma(a23.x, Y2[y1], -a23.y))) * SY[y1];
       const double u2 = fma(a01.x, Y0[y2], fma(a01.y, Y1[y2], fma(a23.x, Y2[y2], -a23.y))) * SY[y2];
       const double u3 = fma(a01.x, Y0[t + 1], fma(a01.y, Y1[t + 1], fma(a23.x, Y2[t + 1], -a23.y))) * SY[t + 1];
+#if FQ_SCAN_ARGMAX
+      // first maximum in the order (cp1, cp2, cp3, cp0): the order in which the decode below used to re-evaluate them
+      int km = rank_key(u1);
+      unsigned wq = 0;
+      { const int k2 = rank_key(u2); if (k2 > km) { km = k2; wq = 1u << 28; } }
+      { const int k3 = rank_key(u3); if (k3 > km) { km = k3; wq = 2u << 28; } }
+      if (item & 0x800u)
+      {
+        const int k0 = rank_key(fma(a01.x, Y0[t], fma(a01.y, Y1[t], fma(a23.x, Y2[t], -a23.y))) * SY[t]);
+        if (k0 > km) { km = k0; wq = 3u << 28; }
+      }
+      if (km > bkey) { bkey = km; bcode = (unsigned)i | wq; }
+#else
       int km = max(max(rank_key(u1), rank_key(u2)), rank_key(u3));
       if (item & 0x800u)
         km = max(km, rank_key(fma(a01.x, Y0[t], fma(a01.y, Y1[t], fma(a23.x, Y2[t], -a23.y))) * SY[t]));
       if (km > bkey) { bkey = km; bcode = (unsigned)i; }
+#endif
     }
     const int mk = __reduce_max_sync(FULL, bkey);
     if (mk <= 0) { status = 1; break; }
@@ -479,13 +493,17 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
     }
     else
     {
-      const unsigned item = m.items[code];
+      const unsigned item = m.items[code & 0x0fffffffu];
       const int t = item >> 12, gf = item & 0x7ff;
       eseg = t + 1;
       const double2 r01 = row_a01(sAb, gf, m.half_ofs), r23 = row_a23(sAb, gf, m.half_ofs);
       w0 = r01.x; w1 = r01.y; w2 = r23.x;
       const double hb = r23.y;                      // b + tol
       h = hb - row_tol;
+#if FQ_SCAN_ARGMAX
+      const unsigned wq = (code >> 28) & 3u;        // the control point the scan ranked highest: cp1, cp2, cp3, cp0
+      y = wq == 0 ? 4 * N + 1 + t : (wq == 1 ? 5 * N + 1 + t : (wq == 2 ? t + 1 : t));
+#else
       const int ys[4] = { 4 * N + 1 + t, 5 * N + 1 + t, t + 1, t };
       y = ys[0];
       int best = -0x7fffffff;
@@ -496,6 +514,7 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
         const int kk = rank_key(fma(w0, m.Y[ys[k]], fma(w1, m.Y[NYP + ys[k]], fma(w2, m.Y[2 * NYP + ys[k]], -hb))) * SY[ys[k]]);
         if (kk > best) { best = kk; y = ys[k]; }
       }
+#endif
     }
     const double sy = SY[y];
     const double gg = (w0 * w0 + w1 * w1 + w2 * w2) * fast_rcp(sy * sy);   // |g|^2 = |w|^2 |TZ[y]|^2
@@ -673,11 +692,13 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
       // further column would not fit the factorisation's storage)
       const bool dep = zz <= fmax(FQ_EPS_DEP * gg, FQ_ZZ_FLOOR) || q >= NW;
       int l = -1;
+#if !FQ_LAZY_LEAVING
       if (t1 < INFINITY)
       {
         const int s2 = __ffs(__ballot_sync(FULL, best == t1)) - 1;
         l = __shfl_sync(FULL, bk, s2);
       }
+#endif
       const double t2 = dep ? INFINITY : viol * rzz;
       if (t1 == INFINITY && t2 == INFINITY)
       {
@@ -720,6 +741,13 @@ __device__ __forceinline__ int gi_loop(const WarpState<D>& m, const double* __re
         break;
       }
       // ---- partial step: active element l leaves.  (l < 0 here means t1/t2 are NaN -- non-finite input: give up)
+#if FQ_LAZY_LEAVING
+      if (t1 < INFINITY)
+      {
+        const int s2 = __ffs(__ballot_sync(FULL, best == t1)) - 1;
+        l = __shfl_sync(FULL, bk, s2);
+      }
+#endif
       if (l < 0) { status = -1; break; }
 #pragma unroll
       for (int s = 0; s < SLOTS; s++)
