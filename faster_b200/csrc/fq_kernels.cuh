@@ -51,6 +51,11 @@
 #define FQ_ITEMS_BY_SEGMENT 0  // 1: the corridor item list written by two lanes per segment (even / odd faces) instead of one
                                // lane per item with a four-step search for its segment.  Measured +3.2 % / +1.3 % SLOWER: off
 #endif
+#ifndef FQ_MAX_N_3CTAS
+#define FQ_MAX_N_3CTAS 15      // largest N whose kernels are compiled for 3 CTAs per SM (<= 168 registers); beyond: 2 CTAs.  N = 14, 15
+                               // run 2 CTAs per SM anyway (shared memory), yet letting the compiler take 223 registers there measured
+                               // -1 % on config 5 (45.3 vs 45.8 M candidates/s, profiles/r02ab_cfg5_ab.log): the bound stays
+#endif
 #ifndef FQ_LAZY_LEAVING
 #define FQ_LAZY_LEAVING 0      // 1: the index of the blocking row (ballot + shuffle) is looked up only when a partial step is taken.
                                // Measured (tools/kernel_ab.py, 3 rounds, profiles/r02aa_kernel_ab.log): no change (0.3862 / 0.5063 ms

@@ -1065,7 +1065,7 @@ __device__ void sweep_tail_select(const FqKernelArgs& a, int c_begin, int count,
 //   FQ_WARP_ADOPT = 1: rows staged per warp (W copies); no barrier after the plan tables are staged, a warp never waits
 //                      for its CTA-mates' last solves.
 template <int N_, bool WHOLE_>
-__global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOLE : FQ_MIN_CTAS_PER_SM) : (N_ <= 15 ? 3 : 2)))
+__global__ void __launch_bounds__(W * 32, (N_ <= 10 ? (WHOLE_ ? FQ_MIN_CTAS_WHOLE : FQ_MIN_CTAS_PER_SM) : (N_ <= FQ_MAX_N_3CTAS ? 3 : 2)))
     fq_solve_kernel_t(const FqKernelArgs a, int* __restrict__ counters)
 {
   using D = Dims<N_, WHOLE_>;
