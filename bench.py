@@ -695,6 +695,47 @@ def parity_block(b, res, solver, torch, capi, dev, n_chk=4):
         hist["within_%g" % s] = {k: int((fl[0]["feasible_" + k] != fl[1]["feasible_" + k]).sum()) for k in ("whole", "safe")}
     out["feasibility_margin_counts"] = hist
     out["feasibility_margin_note"] = "candidates whose flag changes when every row bound moves by -s vs +s (m, m/s, m/s2, m/s3); safe counts include the effect on R"
+    out["proved_on_literal_model"] = proof_sample(full, base["results"], solver)
+    return out
+
+
+def proof_sample(w, rr, solver, n_corr=2, n_cand=24):
+    """A sample of the batch's candidates PROVED on the literal rows of the reference's model (oracle/proofs.py, checker only):
+    "solved" -> the GPU's coefficients are feasible there and carry KKT multipliers (optimal); "not solved" -> the Farkas
+    certificate exported by fq_solve_batch_cert holds.  No solver's verdict enters.  tools/stress_proofs.py is the large run."""
+    out = {"candidates": 0, "solved_proved_optimal": 0, "not_solved_proved_infeasible": 0, "without_proof": 0, "failures": 0}
+    try:
+        from oracle import model_fullspace as mf, proofs
+        rng = np.random.default_rng(4)
+        for j in range(min(n_corr, w["n_prob"])):
+            for kind, N, ff in (("whole", w["N_whole"], True), ("safe", w["N_safe"], False)):
+                base = rr[kind + "_dt_base"][j]
+                x0 = w["x0"][j] if kind == "whole" else rr["R"][j]
+                if not np.isfinite(base) or not np.all(np.isfinite(x0)):
+                    continue
+                po_, fo, Ab = w["poly_ofs_" + kind], w["face_ofs_" + kind], w["Ab_" + kind]
+                polys = [(Ab[fo[q]:fo[q + 1], :3].copy(), Ab[fo[q]:fo[q + 1], 3].copy()) for q in range(po_[j], po_[j + 1])]
+                fac, sig = w["factors_" + kind], w["sigmas_" + kind]
+                dts = fac[rng.integers(0, len(fac), n_cand)] * base
+                sigs = sig[rng.integers(0, len(sig), n_cand)]
+                fg, cg, cog, _ = solver.solve_batch(N, x0, w["xf_" + kind][j], w["lim"][j], polys, dts, sigs, ff, want_coeffs=True)
+                fc, _, cert = solver.solve_batch_cert(N, x0, w["xf_" + kind][j], w["lim"][j], polys, dts, sigs, ff)
+                for i in range(n_cand):
+                    out["candidates"] += 1
+                    model = mf.build(N, x0, w["xf_" + kind][j], w["lim"][j], dts[i], polys, sigs[i], ff)
+                    try:
+                        if fg[i] != fc[i]:
+                            raise AssertionError("kernels disagree")
+                        if fg[i]:
+                            proofs.assert_optimal(model, cog[i], cg[i]); out["solved_proved_optimal"] += 1
+                        elif int(cert[i, 0]) >= 1:
+                            proofs.assert_infeasible(model, N, polys, sigs[i], cert[i]); out["not_solved_proved_infeasible"] += 1
+                        else:
+                            out["without_proof"] += 1
+                    except AssertionError:
+                        out["failures"] += 1
+    except Exception as e:                                    # the checker must never take the measurement down
+        out["error"] = repr(e)[:200]
     return out
 
 
