@@ -317,8 +317,9 @@ protected:
       std::vector<uint8_t> all((size_t)total * N_);
       fq_monotone_sigmas(N_, P_, all.data(), total);
       const long keep = std::min(total, max_sigma_);
-      if (keep < total && verbose_)
-        std::fprintf(stderr, "SolverGurobi(faster_b200): %ld monotone assignments, evaluating an even subset of %ld\n", total, keep);
+      if (keep < total)                            // said once per (N, P, mode): a subset is not the reference's search space
+        std::fprintf(stderr, "SolverGurobi(faster_b200): %ld monotone assignments, evaluating an even subset of %ld "
+                             "(raise max_assignments, or use AUTO / EXACT for the exact MIQP optimum)\n", total, keep);
       for (long k = 0; k < keep; k++)
       {
         const long src = (keep == total || keep <= 1) ? k : (long)((double)k * (total - 1) / (keep - 1) + 0.5);
