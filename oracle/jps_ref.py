@@ -38,3 +38,42 @@ def tables():
     f2 = np.zeros((27, 3, 12), np.int32)
     L.jpsref_tables(ns.ctypes.data_as(C.c_void_p), f1.ctypes.data_as(C.c_void_p), f2.ctypes.data_as(C.c_void_p))
     return ns, f1, f2
+
+
+# ---- the planner layer above the graph search: JPSPlanner<3>::plan over JPS::MapUtil<3> (jps_planner.cpp, map_util.h), compiled
+#      unmodified from /root/reference into oracle/_ref/libjpsplan_ref.so (oracle/jpsplan_ref_wrap.cpp; stub_eigen / stub_ros /
+#      stub_pcl stand in for Eigen, ROS and PCL)
+_PLAN_SO = os.path.join(_HERE, "_ref", "libjpsplan_ref.so")
+
+
+def planner_available():
+    if not os.path.exists(_PLAN_SO) and os.path.exists("/root/reference/thirdparty/jps3d/src/jps_planner/jps_planner.cpp"):
+        subprocess.call(["make", "-C", _HERE, "-s"])
+    return os.path.exists(_PLAN_SO)
+
+
+def plan_world(grid, origin, res, start, goal, use_jps=True, cap=8192):
+    """The reference's world-coordinate plan with its path simplification.  grid int8 [zd,yd,xd] (0 free, 100 occupied,
+    -1 unknown) -> (path float[n,3] start -> goal, raw path float[m,3], planner status: 0 ok, 1 start not free, 2 goal not
+    free, -1 no path)."""
+    L = C.CDLL(_PLAN_SO)
+    L.jpsplanref_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    g = np.ascontiguousarray(grid, np.int8)
+    zd, yd, xd = g.shape
+    o, s, t = (np.ascontiguousarray(np.asarray(v, np.float64)) for v in (origin, start, goal))
+    out, raw = np.zeros((cap, 3)), np.zeros((cap, 3))
+    nr, st = C.c_int(0), C.c_int(0)
+    n = L.jpsplanref_plan(g.ctypes.data, xd, yd, zd, o.ctypes.data, float(res), s.ctypes.data, t.ctypes.data, int(use_jps),
+                          out.ctypes.data, cap, raw.ctypes.data, C.addressof(nr), C.addressof(st))
+    return out[:min(n, cap)].copy(), raw[:min(nr.value, cap)].copy(), st.value
+
+
+def blocked(grid, origin, res, p1, p2):
+    """MapUtil::isBlocked (map_util.h:371-383): a ray-traced cell between p1 and p2 is occupied."""
+    L = C.CDLL(_PLAN_SO)
+    L.jpsplanref_blocked.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    g = np.ascontiguousarray(grid, np.int8)
+    zd, yd, xd = g.shape
+    o, a, b = (np.ascontiguousarray(np.asarray(v, np.float64)) for v in (origin, p1, p2))
+    return bool(L.jpsplanref_blocked(g.ctypes.data, xd, yd, zd, o.ctypes.data, float(res), a.ctypes.data, b.ctypes.data))

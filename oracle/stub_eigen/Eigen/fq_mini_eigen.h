@@ -4,10 +4,13 @@
 // (Eigen is not in this image).  What lives here is plain small-matrix arithmetic -- sums, products, a 3x3 inverse by
 // cofactors, quaternion -> rotation matrix -- written the way Eigen evaluates it (pairwise halves for the reductions);
 // every line of the decomposition ALGORITHM stays the reference's.  Like oracle/stub_boost for the JPS3D graph search.
+// The same stand-in lets the reference's JPS planner layer (jps_planner.cpp, map_util.h: path simplification and ray
+// tracing) compile; oracle/stub_ros and oracle/stub_pcl hold the two empty headers map_util.h includes besides.
 #pragma once
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdint>
 #include <cstddef>
 #include <iostream>
 #include <memory>
@@ -17,6 +20,7 @@
 namespace Eigen
 {
 const int Dynamic = -1;
+const int Infinity = -1;
 enum TransformTraits { Isometry = 1, Affine = 2, AffineCompact = 3, Projective = 4 };
 template <class T>
 using aligned_allocator = std::allocator<T>;
@@ -96,6 +100,22 @@ public:
     for (int i = 0; i < r_; i++)
       for (int j = 0; j < c_; j++) t(j, i) = (*this)(i, j);
     return t;
+  }
+  template <typename T>
+  Matrix<T, R, C> cast() const
+  {
+    Matrix<T, R, C> t = Matrix<T, R, C>::sized(r_, c_);
+    for (int i = 0; i < r_; i++)
+      for (int j = 0; j < c_; j++) t(i, j) = (T)(*this)(i, j);
+    return t;
+  }
+  template <int P>
+  S lpNorm() const
+  { // only the infinity norm is used (map_util.h:353)
+    static_assert(P == Infinity, "only lpNorm<Eigen::Infinity>() is provided");
+    S m = S(0);
+    for (int i = 0; i < size(); i++) { const S a = d_[(std::size_t)i] < S(0) ? -d_[(std::size_t)i] : d_[(std::size_t)i]; if (a > m) m = a; }
+    return m;
   }
   template <int K>
   Matrix<S, K, C> topRows() const

@@ -148,3 +148,45 @@ def test_world_plan_post_processing(built_lib):
                 cidx = np.round((pt - origin) / res - 0.5).astype(int)
                 assert g[cidx[2], cidx[1], cidx[0]] < 100
     assert n_ok >= 3
+
+
+@pytest.mark.skipif(not jps_ref.planner_available(), reason="oracle/_ref/libjpsplan_ref.so is built where /root/reference exists")
+def test_world_plan_equals_the_reference_planner(built_lib):
+    """fq_jps3d_plan_world against the REFERENCE's own planner layer compiled from /root/reference (JPSPlanner<3>::plan over
+    MapUtil<3>: floatToInt / intToFloat, graph search, removeLinePts, removeCornerPts forwards and backwards with the
+    ray-traced line of sight -- jps_planner.cpp:196-295, map_util.h:334-383): the same way points, bit for bit, with JPS and
+    with plain A*; the same refusals (start or goal not free, no path)."""
+    res, origin = 0.25, np.array([-5.0, -5.0, 0.0])
+    n_paths = n_simplified = 0
+    for seed in range(40):
+        g = _forest_grid(50 + seed)
+        rng = np.random.default_rng(seed)
+        s, t = _free_cell(g, rng), _free_cell(g, rng)
+        ws = (np.array(s) + 0.5) * res + origin + rng.uniform(-0.1, 0.1, 3)
+        wt = (np.array(t) + 0.5) * res + origin + rng.uniform(-0.1, 0.1, 3)
+        for use_jps in (True, False):
+            ours, raw_len = capi.jps3d_plan_world(g, origin, res, ws, wt, use_jps)
+            ref, raw, status = jps_ref.plan_world(g, origin, res, ws, wt, use_jps)
+            assert len(ours) == len(ref), (seed, use_jps, status)
+            if len(ref):
+                assert np.array_equal(ours, ref), (seed, use_jps, np.abs(ours - ref).max())
+                assert abs(raw_len - np.sum(np.linalg.norm(np.diff(raw, axis=0), axis=1))) <= 1e-9
+                n_paths += 1
+                n_simplified += len(ref) < len(raw)
+    assert n_paths >= 60 and n_simplified >= 40
+    # refusals: an occupied start, an unknown goal, a walled-in goal
+    g = _forest_grid(7)
+    occ = np.argwhere(g == 100)[0][::-1]
+    free = np.array(_free_cell(g, np.random.default_rng(1)))
+    w_occ, w_free = (occ + 0.5) * res + origin, (free + 0.5) * res + origin
+    for a, b in ((w_occ, w_free), (w_free, w_occ)):
+        ours, _ = capi.jps3d_plan_world(g, origin, res, a, b, True)
+        ref, _, status = jps_ref.plan_world(g, origin, res, a, b, True)
+        assert len(ours) == 0 and len(ref) == 0 and status in (1, 2)
+    g2 = np.zeros((6, 12, 12), np.int8)
+    g2[:, 4:9, 4] = g2[:, 4:9, 8] = g2[:, 4, 4:9] = g2[:, 8, 4:9] = 100
+    g2[0, 4:9, 4:9] = g2[5, 4:9, 4:9] = 100                          # a closed box around the goal
+    a, b = (np.array([1, 1, 2]) + 0.5) * res + origin, (np.array([6, 6, 2]) + 0.5) * res + origin
+    ours, _ = capi.jps3d_plan_world(g2, origin, res, a, b, True)
+    ref, _, status = jps_ref.plan_world(g2, origin, res, a, b, True)
+    assert len(ours) == 0 and len(ref) == 0 and status == -1
