@@ -3,7 +3,8 @@ JPS_Manager::cvxEllipsoidDecomp (faster/src/jps_manager.cpp:80-127) over DecompU
 (thirdparty/DecompROS/DecompUtil/include/decomp_util/{ellipsoid_decomp.h:96-123, line_segment.h:33-38,57-98,156-252,
 decomp_base.h:39-46,83-115}, decomp_geometry/{ellipsoid.h:24-73, polyhedron.h:13-92,114-152, geometric_utils.h:27-35}).
 
-PARITY UNPINNED: the reference needs Eigen (absent from this image) and records no outputs; this restatement follows the
+Checked against the reference's own DecompUtil compiled from /root/reference (oracle/decomp_ref.py, tests/test_decomp_cpu.py);
+it exists because that library cannot travel to a box without /root/reference being needed to rebuild it.  This restatement follows the
 reference statement by statement (same loop order, same strict/non-strict comparisons, epsilon_ = 1e-10 of
 decomp_basis/data_type.h:129).  It pins the product's host implementation (faster_b200/csrc/fq_decomp.cpp).
 Only tests/ and bench tooling may import it.

@@ -5,7 +5,10 @@
  * image) and the reference tree records no outputs for this path.  This file restates the
  * *model* the reference hands to Gurobi and solves it exactly; it is pinned against (i) the closed form of
  * config 1 (N=3, zero degrees of freedom) and (ii) an independent solver (HiGHS) run on the literal
- * full-space model of oracle/model_fullspace.py.  Labelled "CPU restatement of SolverGurobi", never "Gurobi".
+ * full-space model of oracle/model_fullspace.py -- which in turn equals, row by row, the model the reference's own
+ * solverGurobi.cpp builds (compiled over a recording Gurobi stand-in: oracle/solver_ref.py); this file's getDTInitial,
+ * fillX and genNewTraj sweep are compared with the reference's own functions there too (tests/test_reference_solver_cpu.py).
+ * Labelled "CPU restatement of SolverGurobi", never "Gurobi".
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
  * The product (faster_b200/, include/) never links, imports or calls it.

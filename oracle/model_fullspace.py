@@ -8,6 +8,11 @@ condensing -- and hands it to an independent solver (HiGHS, vendored in scipy) f
 interval->polytope assignment sigma.  It is the "second opinion" that pins oracle/fq_oracle.c and, through
 it, the CUDA path.  Only tests/ may import it.
 
+What IS pinned to the reference: `build` is compared, row by row and coefficient by coefficient (exact equality), with the
+model that the reference's own solverGurobi.cpp creates when it is compiled from /root/reference against a recording
+stand-in for the Gurobi API (oracle/solver_ref.py, tests/test_reference_solver_cpu.py).  What stays unpinned is Gurobi's
+numerical solve of that model (tolerances, MIP search).
+
 Variable order (solverGurobi.cpp:72):  z[12*t + k],  k = ax ay az bx by bz cx cy cz dx dy dz,
 p_t(tau) = a tau^3 + b tau^2 + c tau + d  (solverGurobi.cpp:761-788).
 """
@@ -19,8 +24,8 @@ INF = np.inf
 
 def _pos(N, t, tau, ax):            # solverGurobi.cpp:761-767
     r = np.zeros(12 * N)
-    r[12 * t + 0 + ax] = tau ** 3
-    r[12 * t + 3 + ax] = tau ** 2
+    r[12 * t + 0 + ax] = tau * tau * tau     # products in the order the reference writes them: x * tau * tau * tau
+    r[12 * t + 3 + ax] = tau * tau
     r[12 * t + 6 + ax] = tau
     r[12 * t + 9 + ax] = 1.0
     return r
@@ -28,7 +33,7 @@ def _pos(N, t, tau, ax):            # solverGurobi.cpp:761-767
 
 def _vel(N, t, tau, ax):            # solverGurobi.cpp:769-774
     r = np.zeros(12 * N)
-    r[12 * t + 0 + ax] = 3 * tau ** 2
+    r[12 * t + 0 + ax] = 3 * tau * tau           # 3 * x * tau * tau
     r[12 * t + 3 + ax] = 2 * tau
     r[12 * t + 6 + ax] = 1.0
     return r
@@ -112,14 +117,11 @@ def build(N, x0, xf, lim, dt, polys, sigma, force_final=True):
     return (Q, np.array(Aeq), np.array(beq), np.array(Ain), np.array(bin_))
 
 
-def solve_highs(N, x0, xf, lim, dt, polys, sigma, force_final=True, with_status=False):
-    """-> (feasible, cost, coeffs[N,12]).  cost = sum (6a)^2, i.e. Gurobi's ObjVal.  with_status=True appends HiGHS' model
-    status name ("kOptimal", "kInfeasible", or whatever it stopped with: its QP solver sometimes gives up on these
-    degenerate problems, which says nothing about feasibility)."""
+def solve_qp_highs(Q, Aeq, beq, Ain, bin_, with_status=False):
+    """min 0.5 z'Qz  s.t.  Aeq z = beq, Ain z <= bin  by HiGHS (scipy-vendored).  -> (feasible, z[, status name])."""
     from scipy.optimize._highspy import _core as h
-    Q, Aeq, beq, Ain, bin_ = build(N, x0, xf, lim, dt, polys, sigma, force_final)
-    n = 12 * N
-    A = sp.csc_matrix(np.vstack([Aeq, Ain]))
+    n = Q.shape[0]
+    A = sp.csc_matrix(np.vstack([Aeq, Ain]) if len(bin_) else np.asarray(Aeq))
     lo = np.concatenate([beq, np.full(len(bin_), -INF)])
     up = np.concatenate([beq, bin_])
     model = h.HighsModel()
@@ -149,7 +151,18 @@ def solve_highs(N, x0, xf, lim, dt, polys, sigma, force_final=True, with_status=
     st = H.getModelStatus()
     name = str(st).split(".")[-1]
     if st != h.HighsModelStatus.kOptimal:
-        return (False, np.nan, None, name) if with_status else (False, np.nan, None)
+        return (False, None, name) if with_status else (False, None)
     z = np.array(H.getSolution().col_value)
+    return (True, z, name) if with_status else (True, z)
+
+
+def solve_highs(N, x0, xf, lim, dt, polys, sigma, force_final=True, with_status=False):
+    """-> (feasible, cost, coeffs[N,12]).  cost = sum (6a)^2, i.e. Gurobi's ObjVal.  with_status=True appends HiGHS' model
+    status name ("kOptimal", "kInfeasible", or whatever it stopped with: its QP solver sometimes gives up on these
+    degenerate problems, which says nothing about feasibility)."""
+    Q, Aeq, beq, Ain, bin_ = build(N, x0, xf, lim, dt, polys, sigma, force_final)
+    ok, z, name = solve_qp_highs(Q, Aeq, beq, Ain, bin_, with_status=True)
+    if not ok:
+        return (False, np.nan, None, name) if with_status else (False, np.nan, None)
     cost = float(np.sum((6.0 * z.reshape(N, 12)[:, :3]) ** 2))
     return (True, cost, z.reshape(N, 12), name) if with_status else (True, cost, z.reshape(N, 12))

@@ -53,6 +53,32 @@ public:
     d_[0] = (S)a; d_[1] = (S)b; d_[2] = (S)c;
   }
   Matrix(const Quaternion<S>& q);                        // 3x3: the rotation matrix
+  // same coefficients in another static shape: Dynamic <-> fixed sizes, or a vector assigned to its transpose (Eigen allows both)
+  template <typename S2, int R2, int C2, typename std::enable_if<!(std::is_same<S2, S>::value && R2 == R && C2 == C), int>::type = 0>
+  Matrix(const Matrix<S2, R2, C2>& o)
+  {
+    if (!kDyn) { r_ = R; c_ = C; }
+    else if (C == 1) { r_ = o.size(); c_ = 1; }
+    else if (R == 1) { r_ = 1; c_ = o.size(); }
+    else { r_ = R == Dynamic ? o.rows() : R; c_ = C == Dynamic ? o.cols() : C; }
+    init();
+    for (int k = 0; k < size() && k < o.size(); k++) d_[(std::size_t)k] = (S)o[k];
+  }
+  S& x() { return d_[0]; }
+  S& y() { return d_[1]; }
+  S& z() { return d_[2]; }
+  S& w() { return d_[3]; }
+  const S& x() const { return d_[0]; }
+  const S& y() const { return d_[1]; }
+  const S& z() const { return d_[2]; }
+  const S& w() const { return d_[3]; }
+  // four coefficients (Vector4d)
+  template <class A, class B, class D, class E, typename std::enable_if<std::is_arithmetic<A>::value, int>::type = 0>
+  Matrix(const A& a, const B& b, const D& c, const E& d) : r_(R), c_(C)
+  {
+    init();
+    d_[0] = (S)a; d_[1] = (S)b; d_[2] = (S)c; d_[3] = (S)d;
+  }
 
   int rows() const { return r_; }
   int cols() const { return c_; }
@@ -328,5 +354,75 @@ public:
   explicit SelfAdjointEigenSolver(const M&) {}
   Matrix<typename M::Scalar, Dynamic, 1> eigenvalues() const { return Matrix<typename M::Scalar, Dynamic, 1>(); }
 };
+typedef Matrix<double, 2, 1> Vector2d;
 typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<double, 4, 1> Vector4d;
+typedef Matrix<float, 3, 1> Vector3f;
+typedef Matrix<int, 3, 1> Vector3i;
+typedef Matrix<double, Dynamic, 1> VectorXd;
+typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
+typedef Matrix<double, 3, 3> Matrix3d;
+
+// unsupported/Eigen/Polynomials: real roots of a polynomial given by its coefficients in ascending order of degree (the
+// reference's getDTInitial uses it for a quadratic and a cubic, solverGurobi.cpp:697-735).  Eigen takes the eigenvalues of the
+// companion matrix and keeps those whose imaginary part is below 1e-12; this stand-in finds the real roots in closed form
+// (discriminant / trigonometric form) and polishes them with Newton steps on the polynomial itself -- the same numbers to
+// rounding, by a different route.  What is pinned by compiling the reference is everything AROUND the root finder: which
+// polynomials are solved, the float temporaries, MinPositiveElement, the max over the nine times, the division by N.
+template <typename S, int Deg>
+class PolynomialSolver
+{
+public:
+  template <int R, int C>
+  explicit PolynomialSolver(const Matrix<S, R, C>& poly)
+  {
+    for (int i = 0; i < poly.size(); i++) c_.push_back(poly[i]);
+    while (c_.size() > 1 && c_.back() == S(0)) c_.pop_back();       // (Eigen requires a non-zero leading coefficient)
+  }
+  void realRoots(std::vector<S>& out, const S& = S(1e-12)) const
+  {
+    out.clear();
+    const int deg = (int)c_.size() - 1;
+    if (deg == 1) out.push_back(-c_[0] / c_[1]);
+    else if (deg == 2)
+    {
+      const S a = c_[2], b = c_[1], c = c_[0], disc = b * b - S(4) * a * c;
+      if (disc >= S(0))
+      {
+        const S q = -S(0.5) * (b + (b >= S(0) ? std::sqrt(disc) : -std::sqrt(disc)));
+        if (q != S(0)) { out.push_back(q / a); out.push_back(c / q); }
+        else { out.push_back(S(0)); out.push_back(S(0)); }
+      }
+    }
+    else if (deg == 3)
+    {
+      const S a = c_[2] / c_[3], b = c_[1] / c_[3], c = c_[0] / c_[3];         // t^3 + a t^2 + b t + c
+      const S Q = (a * a - S(3) * b) / S(9), Rr = (S(2) * a * a * a - S(9) * a * b + S(27) * c) / S(54);
+      if (Rr * Rr < Q * Q * Q)
+      {
+        const S th = std::acos(Rr / std::sqrt(Q * Q * Q)), m = -S(2) * std::sqrt(Q);
+        const S pi = S(3.14159265358979323846);
+        out.push_back(m * std::cos(th / S(3)) - a / S(3));
+        out.push_back(m * std::cos((th + S(2) * pi) / S(3)) - a / S(3));
+        out.push_back(m * std::cos((th - S(2) * pi) / S(3)) - a / S(3));
+      }
+      else
+      {
+        const S A = -(Rr >= S(0) ? S(1) : S(-1)) * std::cbrt(std::fabs(Rr) + std::sqrt(Rr * Rr - Q * Q * Q));
+        const S B = A != S(0) ? Q / A : S(0);
+        out.push_back((A + B) - a / S(3));
+      }
+    }
+    for (S& r : out)                                                        // Newton polish on the original coefficients
+      for (int it = 0; it < 3; it++)
+      {
+        S f = S(0), df = S(0);
+        for (int k = deg; k >= 0; k--) { df = df * r + f; f = f * r + c_[(std::size_t)k]; }
+        if (df != S(0) && std::isfinite(f / df)) r -= f / df;
+      }
+  }
+
+private:
+  std::vector<S> c_;
+};
 }  // namespace Eigen
