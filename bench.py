@@ -220,6 +220,36 @@ def cpu_pair_rate(n_corr, threads, min_seconds, start=256, fast=True):
     return reps * n_corr * 1024 / el, "%d corridors x 1024 pairs of the cfg4 fixture per pass, %d passes, %.1f s" % (n_corr, reps, el)
 
 
+def reference_code_setup_ms():
+    """What the REFERENCE'S OWN solverGurobi.cpp (compiled from /root/reference over a recording Gurobi stand-in,
+    oracle/_ref/libsolver_ref.so: it travels to the GPU box prebuilt) spends per trial on model set-up alone, single core, no solve:
+    a lower bound on the reference's cost per time-allocation factor (one trial = all assignments of one (corridor, dt))."""
+    try:
+        from oracle import solver_ref as sr
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsolver_ref.so")):
+            return None
+        w = load_cfg4(0, 1)
+        out = {}
+        fd, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)   # the reference prints from its constructor
+        os.dup2(fd, 1)
+        try:
+            for kind, N, ff in (("whole", w["N_whole"], True), ("safe", w["N_safe"], False)):
+                po_, fo, Ab = w["poly_ofs_" + kind], w["face_ofs_" + kind], w["Ab_" + kind]
+                polys = [(Ab[fo[q]:fo[q + 1], :3], Ab[fo[q]:fo[q + 1], 3]) for q in range(po_[0], po_[1])]
+                x0 = w["x0"][0] if kind == "whole" else w["R_oracle"][0]
+                sr.time_setup(N, x0, w["xf_" + kind][0], w["lim"][0], polys, ff, w["DC"], 3)
+                out[kind] = 1e3 * sr.time_setup(N, x0, w["xf_" + kind][0], w["lim"][0], polys, ff, w["DC"], 20)
+        finally:
+            os.dup2(saved, 1)
+            os.close(fd)
+        out["what"] = ("ms per trial of the reference's own createVars/set*Constraints/setObjective code (solverGurobi.cpp:445-455 without "
+                       "optimize()), one core, Gurobi objects replaced by a recording stand-in: a lower bound; one trial covers the "
+                       "%d / %d assignments of one (corridor, time allocation)" % (len(w["sigmas_whole"]), len(w["sigmas_safe"])))
+        return out
+    except Exception as e:
+        return {"error": repr(e)[:160]}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path cannot run (Gurobi is closed source and
     absent); this times the tuned CPU port of the path (oracle/fq_cpu_port.c driving the chain of oracle/pair_oracle.py) on
@@ -253,7 +283,8 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
                              "sample": "%d corridors x 1024 pairs of the cfg4 fixture per step" % n_s, "note": CPU_NOTE,
                              "step_ms_p50_p99": [float(np.percentile(step_s, 50) * 1e3), float(np.percentile(step_s, 99) * 1e3)],
-                             "literal_restatement_pairs_per_s": lit, "os_cpu_count": os.cpu_count()},
+                             "literal_restatement_pairs_per_s": lit, "os_cpu_count": os.cpu_count(),
+                             "reference_code_setup_ms_per_trial": reference_code_setup_ms()},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -562,7 +593,8 @@ def main():
         rate, sample = cpu_pair_rate(args.ref_corridors, threads, args.cpu_seconds)
         lit, _ = cpu_pair_rate(max(1, args.ref_corridors // 8), threads, 2.0, fast=False)
         line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample,
-                                "note": CPU_NOTE, "literal_restatement_pairs_per_s": lit, "os_cpu_count": os.cpu_count()}
+                                "note": CPU_NOTE, "literal_restatement_pairs_per_s": lit, "os_cpu_count": os.cpu_count(),
+                                "reference_code_setup_ms_per_trial": reference_code_setup_ms()}
     if world == 1 and not args.no_other_configs:
         line["other_configs"] = {}
         for name in ("cfg2", "cfg3", "cfg5"):

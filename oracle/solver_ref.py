@@ -109,6 +109,17 @@ def model_for_sigma(md, sigma):
     return md["qdiag"][:nc], np.array(eq), np.array(beq), np.array(ineq), np.array(bin_)
 
 
+def time_setup(N, x0, xf, lim, polys, force_final=True, DC=0.01, n_trials=20):
+    """Seconds per trial of the reference's own model set-up code (no solve): a lower bound on its per-factor cost."""
+    L = _L()
+    ofs, Ab = _pack(polys)
+    x0, xf, lim = _f(x0, 9), _f(xf, 9), _f(lim, 3)
+    L.solverref_time_setup.restype = C.c_double
+    L.solverref_time_setup.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    return L.solverref_time_setup(N, int(bool(force_final)), x0.ctypes.data, xf.ctypes.data, lim.ctypes.data, float(DC), len(polys),
+                                  ofs.ctypes.data, Ab.ctypes.data, int(n_trials)) / n_trials
+
+
 def dt_initial(x0, xf, lim, N):
     x0, xf, lim = _f(x0, 9), _f(xf, 9), _f(lim, 3)
     return float(_L().solverref_dt_initial(int(N), x0.ctypes.data, xf.ctypes.data, lim.ctypes.data))

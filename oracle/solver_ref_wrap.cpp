@@ -8,6 +8,7 @@
 // :122-168) -- and a test can read the model back row by row, or let an independent solver play Gurobi's part in optimize().
 #include "solverGurobi.hpp"
 
+#include <chrono>
 #include <cstring>
 
 void (*fq_grb_optimize_hook)(FqGrbCore*) = nullptr;
@@ -142,6 +143,33 @@ int solverref_model(int N, int force_final, const double* x0, const double* xf, 
   std::memcpy(ind_var, iv.data(), sizeof(int) * nr); std::memcpy(ind_val, ival.data(), sizeof(int) * nr);
   std::memcpy(vtype, vt.data(), nv); std::memcpy(qdiag, qd.data(), sizeof(double) * nv);
   return nr;
+}
+
+// Seconds the reference's own per-trial set-up takes (the body of genNewTraj's loop without the solve, :445-455: findDT,
+// setPolytopesConstraints, setConstraintsX0/Xf, setDynamicConstraints, setObjective, resetX), repeated n_trials times on one
+// solver object like consecutive factors of a sweep.  The stand-in's objects are lighter than Gurobi's, so this is a lower bound
+// on what the reference spends per trial before Gurobi even starts.
+double solverref_time_setup(int N, int force_final, const double* x0, const double* xf, const double* lim, double DC, int P,
+                            const int* face_ofs, const double* Ab, int n_trials)
+{
+  Ref s;
+  setup(s, N, force_final, lim, DC);
+  state a = make_state(x0), b = make_state(xf);
+  s.setX0(a);
+  s.setXf(b);
+  s.setPolytopes(make_polys(P, face_ofs, Ab));
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < n_trials; i++)
+  {
+    s.findDT(1.0 + i);
+    s.setPolytopesConstraints();
+    s.setConstraintsX0();
+    s.setConstraintsXf();
+    s.setDynamicConstraints();
+    s.setObjective();
+    s.resetX();
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 // getDTInitial (:659-759) for (x0, xf, limits, N)
