@@ -21,12 +21,13 @@ import scipy.sparse as sp
 from faster_b200 import capi, corridor as cr
 from oracle import model_fullspace as mf, solver_ref as sr
 
-pytestmark = pytest.mark.skipif(not sr.available(), reason="oracle/_ref/libsolver_ref.so is built where /root/reference exists")
+needs_ref = pytest.mark.skipif(not sr.available(), reason="oracle/_ref/libsolver_ref.so is built where /root/reference exists")
 
 CASES = [("cfg1", 3, 0, True, "uav"), ("cfg2", 10, 3, True, "uav"), ("cfg3", 10, 4, False, "uav"), ("cfg5", 15, 8, True, "ground"),
          ("yaml", 6, 3, True, "uav"), ("safe-small", 6, 2, False, "uav")]
 
 
+@needs_ref
 @pytest.mark.parametrize("name,N,P,ff,profile", CASES)
 def test_literal_model_equals_what_the_reference_code_builds(name, N, P, ff, profile):
     """oracle/model_fullspace.build against the rows the reference's createVars / setBounds / setPolytopesConstraints /
@@ -66,6 +67,7 @@ def test_literal_model_equals_what_the_reference_code_builds(name, N, P, ff, pro
             assert np.array_equal(Ain[nb:], Ain2[perm]) and np.array_equal(bin_[nb:], bin2[perm])
 
 
+@needs_ref
 def test_dt_initial_num_samples_and_fill_x_equal_the_reference_code(oracle):
     """fq_dt_initial against the reference's getDTInitial (:659-759: its float temporaries, MinPositiveElement, the max over
     nine times; the polynomial root finder is a stand-in, oracle/stub_eigen), fq_num_samples / fq_fill_x against its resetX /
@@ -97,6 +99,7 @@ def _highs(q, Aeq, beq, Ain, bin_):
     return ok, z, (float(np.sum(q * z * z)) if ok else np.inf)
 
 
+@needs_ref
 @pytest.mark.parametrize("N,P,ff", [(5, 2, True), (4, 3, True), (5, 2, False), (4, 0, True)])
 def test_gen_new_traj_loop_of_the_reference_with_an_independent_solver(oracle, N, P, ff):
     """The reference's genNewTraj (:426-477) compiled from its source, HiGHS + enumeration of the binaries answering optimize():
@@ -121,6 +124,7 @@ def test_gen_new_traj_loop_of_the_reference_with_an_independent_solver(oracle, N
     assert n_solved >= 2
 
 
+@needs_ref
 def test_reference_loop_refusals(oracle):
     """No factor works: every factor is tried, `solved` is false (:445-472).  StopExecution() before genNewTraj(): no trial at
     all and the flag is reset (:30-39,:445,:474) -- what tests/test_shim_cpu.py asserts of the drop-in class."""
@@ -133,3 +137,28 @@ def test_reference_loop_refusals(oracle):
     assert not ref["solved"] and not ora["solved"] and ref["trials"] == 3 == ora["trials"] and ref["n_optimize"] == 3
     stopped = sr.gen_new_traj(N, pb["x0"], pb["xf"], pb["lim"], pb["polys"], 0.01, 1.0, 3.0, 1.0, _highs, ff, stop_first=True)
     assert not stopped["solved"] and stopped["trials"] == 0 and stopped["n_optimize"] == 0
+
+
+def test_cpu_restatement_matches_the_committed_reference_sweeps(oracle):
+    """tests/golden/reference_sweeps.json holds what THE REFERENCE'S OWN genNewTraj returned here (compiled from /root/reference,
+    HiGHS answering optimize(); tools/make_reference_sweep_goldens.py).  The CPU restatement's sweep -- the checker of the CUDA
+    path in the GPU tests -- reproduces it wherever this test runs, including boxes without /root/reference: solved, trials_,
+    dt_, factor_that_worked_, coefficients, the sample count and the first and last sampled state."""
+    import json
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sweeps.json")))
+    n_solved = n_unsolved = 0
+    for c in fx["cases"]:
+        polys = [(np.array(p["A"]), np.array(p["b"])) for p in c["polys"]]
+        o = oracle.gen_new_traj(c["N"], c["x0"], c["xf"], c["lim"], polys, c["DC"], *c["window"], None, c["force_final"])
+        assert o["solved"] == c["solved"] and o["trials"] == c["trials"] and o["dt"] == c["dt"], (c["N"], c["P"], o["trials"], c["trials"])
+        if not c["solved"]:
+            n_unsolved += 1
+            continue
+        n_solved += 1
+        assert o["factor"] == c["factor"]
+        co = np.array(c["coeffs"])
+        assert np.abs(o["coeffs"] - co).max() <= 1e-6 * max(1.0, np.abs(co).max())
+        X = capi.fill_x(c["N"], o["coeffs"], o["dt"], c["DC"])
+        assert len(X) == c["n_samples"]
+        assert np.abs(X[0] - np.array(c["first_sample"])).max() <= 1e-5 and np.abs(X[-1] - np.array(c["last_sample"])).max() <= 1e-5
+    assert n_solved >= 6 and n_unsolved >= 2
