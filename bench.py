@@ -240,8 +240,14 @@ def reference_code_setup_ms():
                 sr.time_setup(N, x0, w["xf_" + kind][0], w["lim"][0], polys, ff, w["DC"], 3)
                 out[kind] = 1e3 * sr.time_setup(N, x0, w["xf_" + kind][0], w["lim"][0], polys, ff, w["DC"], 20)
         finally:
+            try:
+                import ctypes
+                ctypes.CDLL(None).fflush(None)                    # whatever the C++ side still buffers goes to /dev/null too
+            except Exception:
+                pass
             os.dup2(saved, 1)
             os.close(fd)
+            os.close(saved)
         out["what"] = ("ms per trial of the reference's own createVars/set*Constraints/setObjective code (solverGurobi.cpp:445-455 without "
                        "optimize()), one core, Gurobi objects replaced by a recording stand-in: a lower bound; one trial covers the "
                        "%d / %d assignments of one (corridor, time allocation)" % (len(w["sigmas_whole"]), len(w["sigmas_safe"])))
