@@ -16,6 +16,9 @@
 #define SOLVER_GUROBI_HPP
 
 #include "faster_b200.h"
+#if __has_include(<Eigen/Dense>)
+#include <Eigen/Dense>             // the reference's faster_types.hpp relies on its includer for Eigen (solverGurobi.hpp:11 there)
+#endif
 #if __has_include("faster_types.hpp")
 #include "faster_types.hpp"        // the reference's own `state` when this header lives in the reference tree
 #else

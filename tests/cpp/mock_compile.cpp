@@ -3,6 +3,14 @@
 // setDistances' signature (solverGurobi.hpp:100), resetX.
 #include "solverGurobi.hpp"
 #include <cstdio>
+#ifdef FQ_EXPECT_REFERENCE_TYPES
+// the reference's own headers are in use, not the look-alikes: their include guards are defined and `state` has the
+// reference's printHorizontal (faster_types.hpp:160-164)
+#if !defined(DECOMP_POLYGON_H) || !defined(DATA_TYPE_H)
+#error "DecompUtil's own polyhedron.h / data_type.h were expected"
+#endif
+static_assert(std::is_same<decltype(&state::printHorizontal), void (state::*)()>::value, "the reference's state was expected");
+#endif
 
 struct Probe : SolverGurobi
 {
