@@ -1,0 +1,39 @@
+"""bench.py's contract, as far as it can be checked without a GPU: the reference arm (`--impl reference`) runs on host cores
+only, prints exactly ONE JSON line on stdout and carries the keys the driver reads; under a 2-rank launch only rank 0 speaks."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+        "data", "config", "cpu_baseline", "e2e")
+
+
+def _run(extra_env=None, gpus=1):
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    env.update(extra_env or {})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(gpus), "--steps", "2",
+                        "--warmup", "1", "--ref-corridors", "8"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-800:]
+    return [ln for ln in p.stdout.splitlines() if ln.strip()]
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    lines = _run()
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference"
+    for k in BASE:
+        assert k in d, k
+    assert d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert "cfg4" in d["config"]["workload"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == d["unit"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] / 1e3 - 8 * 1024) < 1e-6 * 8 * 1024      # 8 corridors x 1024 pairs per step
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    assert _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, gpus=2) == []
