@@ -37,3 +37,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 
 def test_reference_arm_other_ranks_stay_silent():
     assert _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, gpus=2) == []
+
+
+def test_gpu_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: without a CUDA device the product arm exits non-zero and says why; nothing is printed on stdout."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=600, env=env, cwd=ROOT)
+    assert p.returncode != 0 and "CUDA" in p.stderr and p.stdout.strip() == ""
