@@ -5,7 +5,9 @@
 // cofactors, quaternion -> rotation matrix -- written the way Eigen evaluates it (pairwise halves for the reductions);
 // every line of the decomposition ALGORITHM stays the reference's.  Like oracle/stub_boost for the JPS3D graph search.
 // The same stand-in lets the reference's JPS planner layer (jps_planner.cpp, map_util.h: path simplification and ray
-// tracing) compile; oracle/stub_ros and oracle/stub_pcl hold the two empty headers map_util.h includes besides.
+// tracing) compile; oracle/stub_ros and oracle/stub_pcl hold the two empty headers map_util.h includes besides.  And the
+// reference's solver class itself (faster/src/solverGurobi.cpp with faster_types.hpp: Vector3d states, MatrixXd polytope
+// rows, the polynomial solver of getDTInitial) over oracle/stub_gurobi.
 #pragma once
 #include <algorithm>
 #include <array>
