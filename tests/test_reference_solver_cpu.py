@@ -85,6 +85,23 @@ def test_dt_initial_num_samples_and_fill_x_equal_the_reference_code(oracle):
         assert a == b or abs(a - b) <= 2e-7 * abs(b), (k, a, b)  # float temporaries: one float ulp at most
         n_exact += a == b
     assert n_exact >= 396
+    z = np.zeros(9)
+    edge = [(z, z, [5, 5, 8], 10)]                                # identical rest states: 0 (findDT then takes 2 DC)
+    far = z.copy(); far[0] = 1e6
+    edge.append((z, far, [5, 5, 8], 10))                          # "no solution" branch: > 10000 s -> 0 (:752-756)
+    nm = z.copy(); nm[:3] = [1e-9, -1e-9, 0.0]
+    edge.append((z, nm, [5, 5, 8], 10))
+    fast = z.copy(); fast[3:6] = [4.9, -4.9, 0.0]
+    near = z.copy(); near[:3] = [0.5, -0.5, 0.1]
+    edge.append((fast, near, [5, 5, 8], 6))
+    acc = z.copy(); acc[6:9] = [2.9, -2.9, 1.0]
+    back = z.copy(); back[:3] = [-3, 3, 1]
+    edge.append((acc, back, [5, 3, 5], 10))
+    away = z.copy(); away[3] = 1.0
+    goal = z.copy(); goal[0] = -2.0
+    edge.append((away, goal, [1.4, 1.4, 5.0], 15))
+    for x0, xf, lim, N in edge:
+        assert capi.dt_initial(x0, xf, lim, N) == sr.dt_initial(x0, xf, lim, N) == oracle.dt_initial(x0, xf, lim, N)
     for seed, (N, dt, DC) in enumerate([(10, 0.37, 0.01), (6, 0.2051, 0.01), (15, 0.113, 0.01), (3, 0.5, 0.05), (10, 0.0012, 0.01)]):
         co = np.random.default_rng(seed).normal(size=(N, 12))
         ref = sr.fill_x(N, co, dt, DC)
