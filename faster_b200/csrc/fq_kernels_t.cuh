@@ -57,7 +57,11 @@ __host__ __device__ inline int per_warp_bytes(int item_cap) { return D::PER_WARP
 __device__ __forceinline__ double fast_rcp(double x)
 {
   double r;
+#ifdef FQ_EMULATE_ON_HOST          // tests/cpp/kernel_emu.cpp: this source under a host-side warp emulation (no inline PTX there)
+  r = (double)(float)(1.0 / x);
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
   r = fma(fma(-x, r, 1.0), r, r);
   r = fma(fma(-x, r, 1.0), r, r);
   return r;
@@ -65,7 +69,11 @@ __device__ __forceinline__ double fast_rcp(double x)
 __device__ __forceinline__ double fast_rsqrt(double x)
 {
   double r;
+#ifdef FQ_EMULATE_ON_HOST
+  r = (double)(float)(1.0 / sqrt(x));
+#else
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
   const double hx = 0.5 * x;
   r = fma(fma(-hx * r, r, 0.5), r, r);
   r = fma(fma(-hx * r, r, 0.5), r, r);
@@ -1290,6 +1298,7 @@ size_t smem_bytes_t(int max_faces, int item_cap, int sab_copies = (FQ_WARP_ADOPT
          (40 * sab_copies + W * 32) * 4 + 16;
 }
 
+#ifndef FQ_EMULATE_ON_HOST
 // `counters`: a.n_prob ints of device memory, zeroed here on `stream`
 template <int N_, bool WHOLE_>
 cudaError_t launch_t(const FqKernelArgs& a, long long total_cand_hint, cudaStream_t stream, int* counters, int sm_count)
@@ -1338,4 +1347,5 @@ cudaError_t launch_t(const FqKernelArgs& a, long long total_cand_hint, cudaStrea
   kern<<<(unsigned)grid, W * 32, smem, stream>>>(a, counters);
   return cudaGetLastError();
 }
+#endif
 }  // namespace fqt

@@ -1,0 +1,142 @@
+// TEST INFRASTRUCTURE ONLY -- the product's kernel SOURCE (faster_b200/csrc/fq_kernels_t.cuh: fq_solve_kernel_t, the persistent
+// warp-per-candidate dual active-set solver) compiled for the host and executed under the lock-step block emulation of
+// simt_emu/simt_emu.h: 128 fibres = one CTA of four warps, claim counters, staging, item lists, the whole active-set iteration,
+// run instruction for instruction as written for the GPU (the two MUFU seeds are replaced by a float-precision seed, the launch
+// function is not compiled).  tests/test_kernel_emu_cpu.py compares its answers with the CPU restatement -- a check of the
+// kernel's LOGIC that needs no GPU.  It is not a CPU path of the product and is far too slow to be one.
+#define FQ_EMULATE_ON_HOST 1
+#include "simt_emu/cuda_runtime.h"
+
+#include "fq_kernels.cuh"
+#include "fq_kernels_t.cuh"
+
+#include <cstdio>
+
+namespace fqt
+{ // the kernel declares its dynamic shared array inside namespace fqt: this is that array (one block runs at a time)
+alignas(16) unsigned char smem_raw[232 * 1024];
+}
+
+namespace simt
+{
+Block* g = nullptr;
+
+static void trampoline()
+{
+  Block* b = g;
+  b->entry(b->arg);
+  self().wait = DONE;
+  swapcontext(&self().ctx, &b->sched);
+}
+
+void run_block(dim3 grid, dim3 block, uint3 bidx, void (*entry)(void*), void* arg, size_t stack_bytes)
+{
+  Block b;
+  b.grid = grid; b.block = block; b.bidx = bidx; b.entry = entry; b.arg = arg;
+  const int n = (int)block.x;
+  b.f.resize((size_t)n);
+  g = &b;
+  for (int i = 0; i < n; i++)
+  {
+    Fiber& f = b.f[(size_t)i];
+    f.tid = (unsigned)i;
+    f.stack.resize(stack_bytes);
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack.data();
+    f.ctx.uc_stack.ss_size = f.stack.size();
+    f.ctx.uc_link = &b.sched;
+    makecontext(&f.ctx, trampoline, 0);
+  }
+  for (;;)
+  {
+    bool ran = false, all_done = true;
+    for (int i = 0; i < n; i++)
+    {
+      if (b.f[(size_t)i].wait != NONE) continue;
+      b.cur = i;
+      swapcontext(&b.sched, &b.f[(size_t)i].ctx);
+      ran = true;
+    }
+    // a warp whose live lanes all wait on a collective goes on
+    for (int w = 0; w < n; w += 32)
+    {
+      int waiting = 0, live = 0;
+      for (int l = w; l < w + 32 && l < n; l++) { live += b.f[(size_t)l].wait != DONE; waiting += b.f[(size_t)l].wait == WARP; }
+      if (live && waiting == live)
+        for (int l = w; l < w + 32 && l < n; l++) if (b.f[(size_t)l].wait == WARP) b.f[(size_t)l].wait = NONE;
+    }
+    int at_barrier = 0, live = 0, any = 0;
+    for (int i = 0; i < n; i++)
+    {
+      const int wt = b.f[(size_t)i].wait;
+      live += wt != DONE; at_barrier += wt == BLOCK; all_done = all_done && wt == DONE;
+      if (wt == BLOCK) any |= b.f[(size_t)i].pred;
+    }
+    if (live && at_barrier == live)
+    {
+      b.block_or = any;
+      for (int i = 0; i < n; i++) if (b.f[(size_t)i].wait == BLOCK) { b.f[(size_t)i].wait = NONE; b.f[(size_t)i].pred = 0; }
+    }
+    if (all_done) break;
+    if (!ran)
+    { // nobody could run and nothing was released in the previous round: a deadlock in the emulated code
+      bool released = false;
+      for (int i = 0; i < n; i++) released = released || b.f[(size_t)i].wait == NONE;
+      if (!released) { std::fprintf(stderr, "simt_emu: deadlock (divergent collective?)\n"); std::abort(); }
+    }
+  }
+  g = nullptr;
+}
+}  // namespace simt
+
+namespace
+{
+struct Call { FqKernelArgs a; int* counters; };
+template <int N, bool WHOLE>
+void entry(void* p)
+{
+  Call* c = static_cast<Call*>(p);
+  fqt::fq_solve_kernel_t<N, WHOLE>(c->a, c->counters);
+}
+template <int N, bool WHOLE>
+int run(Call& c)
+{
+  if (fqt::smem_bytes_t<N, WHOLE>(c.a.max_faces, c.a.item_cap) > sizeof(fqt::smem_raw)) return -2;
+  simt::run_block(dim3(1), dim3(fqt::W * 32), uint3{ 0, 0, 0 }, entry<N, WHOLE>, &c);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+// One CTA of the product kernel over a multi-problem batch laid out like fq_solve_multi (include/faster_b200.h); plan tables
+// TZ / T0 / FT from fq_plan_tables.  Returns 0, -1 for an (N, mode) the harness does not instantiate, -2 if the batch needs more
+// shared memory than a CTA has.
+int emu_solve_multi(int N, int force_final, const double* TZ, const double* T0, const double* FT, int n_prob, const double* x0,
+                    const double* xf, const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab, int max_faces,
+                    int max_poly_faces, const int* cand_ofs, const double* dt, const uint8_t* sigma, double row_tol, uint8_t* feasible,
+                    double* cost, double* coeffs, int32_t* iters)
+{
+  Call c;
+  std::memset(&c.a, 0, sizeof(c.a));
+  const int ne = force_final ? 3 : 2;
+  c.a.N = N; c.a.force_final = force_final; c.a.ne = ne; c.a.nz = N - ne; c.a.nw = 3 * (N - ne); c.a.NY = 6 * N + 1;
+  c.a.TZ = TZ; c.a.T0 = T0; c.a.FT = FT;
+  c.a.n_prob = n_prob; c.a.x0 = x0; c.a.xf = xf; c.a.lim = lim; c.a.poly_ofs = poly_ofs; c.a.face_ofs = face_ofs; c.a.Ab = Ab;
+  c.a.max_faces = max_faces > 0 ? max_faces : 1;
+  c.a.item_cap = N * (max_poly_faces > 0 ? max_poly_faces : c.a.max_faces);
+  c.a.cand_ofs = cand_ofs; c.a.dt = dt; c.a.sigma = sigma;
+  c.a.feasible = feasible; c.a.cost = cost; c.a.coeffs = coeffs; c.a.iters = iters; c.a.row_tol = row_tol;
+  std::vector<int> counters((size_t)n_prob + 1, 0);
+  c.counters = counters.data();
+  const int key = N * 2 + (force_final ? 1 : 0);
+  switch (key)
+  {
+    case 4 * 2 + 0: return run<4, false>(c);
+    case 6 * 2 + 1: return run<6, true>(c);
+    case 10 * 2 + 1: return run<10, true>(c);
+    case 10 * 2 + 0: return run<10, false>(c);
+    case 15 * 2 + 1: return run<15, true>(c);
+    default: return -1;
+  }
+}
+}

@@ -1,0 +1,160 @@
+"""The product's CUDA kernel SOURCE, executed without a GPU: faster_b200/csrc/fq_kernels_t.cuh (fq_solve_kernel_t: persistent CTAs,
+claim counters, row staging, item lists, the warp-per-candidate dual active-set iteration) is compiled for the host and run under
+a lock-step emulation of one thread block (tests/cpp/simt_emu/: every CUDA thread is a fibre, warp collectives and block barriers
+are rendezvous points) and compared with the CPU restatement.  This checks the kernel's LOGIC in a container that has no GPU --
+including compile-time variants of it -- and is what the `-m gpu` parity tests then confirm on the hardware.  It is test
+infrastructure, not a CPU path of the product (the library still refuses to work without a GPU) and ~10^4 times too slow to be one."""
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from faster_b200 import capi, corridor as cr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_libs = {}
+
+
+def _emu(defines=()):
+    """The harness built with the given -D flags (cached per flag set under tests/cpp/_build, rebuilt when a source is newer)."""
+    key = hashlib.sha1(" ".join(defines).encode()).hexdigest()[:10]
+    if key in _libs:
+        return _libs[key]
+    out = os.path.join(ROOT, "tests", "cpp", "_build", "libkernel_emu_%s.so" % key)
+    srcs = [os.path.join(ROOT, "tests", "cpp", "kernel_emu.cpp"), os.path.join(ROOT, "tests", "cpp", "simt_emu", "simt_emu.h"),
+            os.path.join(ROOT, "faster_b200", "csrc", "fq_kernels_t.cuh"), os.path.join(ROOT, "faster_b200", "csrc", "fq_kernels.cuh")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w"] + ["-D" + d for d in defines] +
+                              ["-I", os.path.join(ROOT, "tests", "cpp"), "-I", os.path.join(ROOT, "tests", "cpp", "simt_emu"),
+                               "-I", os.path.join(ROOT, "faster_b200", "csrc"), "-I", os.path.join(ROOT, "include"), srcs[0], "-o", out])
+    L = C.CDLL(out)
+    L.emu_solve_multi.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + \
+                                 [C.c_void_p] * 3 + [C.c_double] + [C.c_void_p] * 4
+    _libs[key] = L
+    return L
+
+
+def solve_multi(L, N, ff, x0, xf, lim, poly_ofs, face_ofs, Ab, cand_ofs, dts, sigmas, row_tol=1e-8, max_faces=None, max_poly_faces=None):
+    """fq_solve_multi's layout through ONE emulated CTA of the product kernel -> (feasible, cost, coeffs, iters)."""
+    TZ, T0, FT = [np.ascontiguousarray(t, np.float64) for t in capi.plan_tables(N, ff)]
+    c = lambda a, t: np.ascontiguousarray(a, t)
+    x0, xf, lim, Ab, dts = c(x0, np.float64), c(xf, np.float64), c(lim, np.float64), c(Ab, np.float64), c(dts, np.float64)
+    poly_ofs, face_ofs, cand_ofs, sig = c(poly_ofs, np.int32), c(face_ofs, np.int32), c(cand_ofs, np.int32), c(sigmas, np.uint8)
+    n_prob, n = len(cand_ofs) - 1, int(cand_ofs[-1])
+    if max_faces is None:
+        max_faces = int(max(face_ofs[poly_ofs[j + 1]] - face_ofs[poly_ofs[j]] for j in range(n_prob)))
+    if max_poly_faces is None:
+        max_poly_faces = int(np.diff(face_ofs).max()) if len(face_ofs) > 1 else 0
+    feas, cost, co, it = np.zeros(n, np.uint8), np.zeros(n), np.zeros((n, N, 12)), np.zeros(n, np.int32)
+    rc = L.emu_solve_multi(N, int(bool(ff)), TZ.ctypes.data, T0.ctypes.data, FT.ctypes.data, n_prob, x0.ctypes.data, xf.ctypes.data,
+                           lim.ctypes.data, poly_ofs.ctypes.data, face_ofs.ctypes.data, Ab.ctypes.data, max_faces, max_poly_faces,
+                           cand_ofs.ctypes.data, dts.ctypes.data, sig.ctypes.data, float(row_tol), feas.ctypes.data, cost.ctypes.data,
+                           co.ctypes.data, it.ctypes.data)
+    assert rc == 0, rc
+    return feas, cost, co, it
+
+
+def _batch(oracle, N, P, ff, profile, seeds, n_sig, factors, rng):
+    x0, xf, lim, po_, fo, rows, co_, dts, sigs = [], [], [], [0], [0], [], [0], [], []
+    for seed in seeds:
+        pb = cr.make_corridor(seed, P, N, profile, ff)
+        allm = cr.monotone_sigmas(N, P) if P <= 4 else cr.sample_monotone_sigmas(N, P, 200, rng)
+        sig = np.vstack([allm[rng.choice(len(allm), min(n_sig - 2, len(allm)), replace=False)], rng.integers(0, P, (2, N)).astype(np.uint8)])
+        base = max(oracle.dt_initial(pb["x0"], pb["xf"], pb["lim"], N), 0.02)
+        x0.append(pb["x0"]); xf.append(pb["xf"]); lim.append(pb["lim"])
+        for A, b in pb["polys"]:
+            rows.append(np.hstack([A, np.asarray(b)[:, None]])); fo.append(fo[-1] + len(b))
+        po_.append(po_[-1] + P)
+        dts.append(np.repeat(np.asarray(factors) * base, len(sig))); sigs.append(np.tile(sig, (len(factors), 1)))
+        co_.append(co_[-1] + len(dts[-1]))
+    return (np.array(x0), np.array(xf), np.array(lim), np.array(po_), np.array(fo), np.vstack(rows), np.array(co_), np.concatenate(dts),
+            np.vstack(sigs))
+
+
+def _check(oracle, N, ff, b, got, tol=1e-9):
+    out = oracle.solve_multi_port(N, ff, *b, threads=4, want_coeffs=True)      # the CPU restatement, per problem
+    f, c, cc = out[0], out[1], out[2]
+    assert np.array_equal(got[0], f), "flags differ at %s" % np.flatnonzero(got[0] != f)[:8]
+    ok = f.astype(bool)
+    assert ok.any() and (~ok).any()
+    assert (np.abs(got[1][ok] - c[ok]) / np.maximum(1e-12, np.abs(c[ok]))).max() <= tol
+    assert np.isinf(got[1][~ok]).all()
+    assert np.abs(got[2][ok] - cc[ok].reshape(-1, N, 12)).max() <= 1e-7
+    return int(ok.sum())
+
+
+def test_demo_corridor_sweep_through_the_emulated_kernel(oracle, demo_corridor):
+    """__graft_entry__.smoke()'s batch (the reference demo's corridor, 4 time allocations x 66 assignments) without a GPU."""
+    fx = demo_corridor
+    N = fx["N"]
+    sig = cr.monotone_sigmas(N, 3)
+    dts, sigs = np.repeat(np.array([0.6, 0.8, 1.0, 1.5]), len(sig)), np.tile(sig, (4, 1))
+    fo = np.concatenate([[0], np.cumsum([len(b) for _, b in fx["polys"]])])
+    Ab = np.vstack([np.hstack([A, np.asarray(b)[:, None]]) for A, b in fx["polys"]])
+    got = solve_multi(_emu(), N, True, [fx["x0"]], [fx["xf"]], [fx["lim"]], [0, 3], fo, Ab, [0, len(dts)], dts, sigs)
+    f, c, co = oracle.solve_batch(N, fx["x0"], fx["xf"], fx["lim"], fx["polys"], dts, sigs, True, True, threads=4)
+    assert np.array_equal(got[0], f) and f.sum() == 61
+    ok = f.astype(bool)
+    assert (np.abs(got[1][ok] - c[ok]) / np.abs(c[ok])).max() < 1e-9 and np.abs(got[2][ok] - co[ok]).max() < 1e-7
+    assert (got[3][ok] >= 0).all() and (got[3] != 0).all()
+
+
+@pytest.mark.parametrize("name,N,P,ff,profile", [("cfg2", 10, 3, True, "uav"), ("cfg3", 10, 4, False, "uav"), ("cfg5", 15, 8, True, "ground"),
+                                                  ("yaml", 6, 3, True, "uav"), ("small-safe", 4, 2, False, "uav")])
+def test_emulated_kernel_matches_the_cpu_restatement(oracle, name, N, P, ff, profile):
+    """Several corridors per launch (warps adopt problems and claim candidates dynamically, as on the GPU), monotone and
+    arbitrary assignments, whole and safe mode, one and two slots per lane (N = 15: 36 unknowns)."""
+    rng = np.random.default_rng(len(name) + N)
+    b = _batch(oracle, N, P, ff, profile, [9100 + 7 * N + k for k in range(3)], 10, [0.3, 0.6, 1.0, 1.5, 2.0, 3.0, 5.0], rng)
+    got = solve_multi(_emu(), N, ff, *b)
+    n_ok = _check(oracle, N, ff, b, got)
+    assert n_ok >= 10
+
+
+def test_compile_time_variants_compute_the_same_thing(oracle):
+    """The ratio test's minimum through redux.sync on the order-preserving image of the doubles (on) against the shuffle tree
+    (FQ_MIN_REDUX=0), and the four variants measured neutral or slower on the B200 and left off (FQ_LAZY_LEAVING,
+    FQ_SCAN_ARGMAX, FQ_GI_HOIST, FQ_ITEMS_BY_SEGMENT): every one of them returns the same flags, the same iteration counts and
+    the same costs and coefficients BIT FOR BIT as the default build -- they reorganise the work, not the arithmetic."""
+    rng = np.random.default_rng(12)
+    base = {}
+    for N, P, ff in ((10, 3, True), (10, 4, False), (15, 8, True)):
+        b = _batch(oracle, N, P, ff, "uav" if N < 15 else "ground", [9300 + N + k for k in range(2)], 8, [1.0, 2.0, 3.0, 6.0], rng)
+        base[(N, ff)] = (b, solve_multi(_emu(), N, ff, *b))
+    for flags in (["FQ_MIN_REDUX=0"], ["FQ_LAZY_LEAVING=1"], ["FQ_SCAN_ARGMAX=1"], ["FQ_GI_HOIST=1"], ["FQ_ITEMS_BY_SEGMENT=1"],
+                  ["FQ_LAZY_LEAVING=1", "FQ_SCAN_ARGMAX=1", "FQ_GI_HOIST=1", "FQ_ITEMS_BY_SEGMENT=1", "FQ_MIN_REDUX=0"]):
+        L = _emu(flags)
+        for (N, ff), (b, ref) in base.items():
+            got = solve_multi(L, N, ff, *b)
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[3], ref[3]), (flags, N, ff)
+            assert got[1].tobytes() == ref[1].tobytes() and got[2].tobytes() == ref[2].tobytes(), (flags, N, ff)
+
+
+def test_guards_of_the_kernel(oracle, demo_corridor):
+    """What the kernel must refuse by itself because the device-pointer entry cannot validate it on the host: non-finite or
+    non-positive inputs (candidate reported not solved, iters = -1), a row list that does not fit the caller's size hint
+    (iters = -2) -- never an out-of-bounds access (the emulation runs under the host's address-space rules)."""
+    fx = demo_corridor
+    N = fx["N"]
+    sig = cr.monotone_sigmas(N, 3)[:6]
+    fo = np.concatenate([[0], np.cumsum([len(b) for _, b in fx["polys"]])])
+    Ab = np.vstack([np.hstack([A, np.asarray(b)[:, None]]) for A, b in fx["polys"]])
+    dts = np.array([0.8, np.nan, -1.0, 0.0, 1.0, np.inf])
+    got = solve_multi(_emu(), N, True, [fx["x0"]], [fx["xf"]], [fx["lim"]], [0, 3], fo, Ab, [0, 6], dts, sig)
+    assert list(got[3][[1, 2, 3, 5]]) == [-1, -1, -1, -1] and not got[0][[1, 2, 3, 5]].any() and np.isinf(got[1][[1, 2, 3, 5]]).all()
+    assert got[3][0] > 0 and got[3][4] > 0
+    x0 = np.array(fx["x0"], float)
+    x0[4] = np.inf
+    got = solve_multi(_emu(), N, True, [x0], [fx["xf"]], [fx["lim"]], [0, 3], fo, Ab, [0, 2], [0.8, 1.0], sig[:2])
+    assert not got[0].any() and (got[3] == -1).all()
+    # a size hint smaller than the problem's rows: the staging area is never overrun, the candidates are marked
+    got = solve_multi(_emu(), N, True, [fx["x0"]], [fx["xf"]], [fx["lim"]], [0, 3], fo, Ab, [0, 2], [0.8, 1.0], sig[:2], max_faces=int(fo[-1]) - 3)
+    assert not got[0].any() and (got[3] == -2).all()
+    # a per-polytope hint that makes the item list too short for this assignment
+    got = solve_multi(_emu(), N, True, [fx["x0"]], [fx["xf"]], [fx["lim"]], [0, 3], fo, Ab, [0, 2], [0.8, 1.0], sig[:2], max_poly_faces=2)
+    assert not got[0].any() and (got[3] == -2).all()
