@@ -108,6 +108,22 @@ int run(Call& c)
 }  // namespace
 
 extern "C" {
+int emu_solve_multi(int N, int force_final, const double* TZ, const double* T0, const double* FT, int n_prob, const double* x0,
+                    const double* xf, const double* lim, const int* poly_ofs, const int* face_ofs, const double* Ab, int max_faces,
+                    int max_poly_faces, const int* cand_ofs, const double* dt, const uint8_t* sigma, double row_tol, uint8_t* feasible,
+                    double* cost, double* coeffs, int32_t* iters);
+// options of the next emu_solve_multi call (what fq_launch_solve_ctx sets for the drop-in class's sweeps, fq_capi.cu):
+//   early_exit != 0: "first feasible factor wins" (first_feasible + sorted_dt: candidates whose dt exceeds the smallest feasible dt
+//                    found so far are not evaluated, iters = -3);
+//   sweep_n_sigma > 0: single-problem sweep, dt-major with that many assignments per time allocation: the warp that finishes the
+//                    last candidate runs genNewTraj's selection inside the kernel and writes sweep_idx[2] / sweep_win[1 + 12 N].
+static int g_early_exit = 0, g_sweep_n_sigma = 0;
+static int* g_sweep_idx = nullptr;
+static double* g_sweep_win = nullptr;
+void emu_set_sweep(int early_exit, int sweep_n_sigma, int* sweep_idx, double* sweep_win)
+{
+  g_early_exit = early_exit; g_sweep_n_sigma = sweep_n_sigma; g_sweep_idx = sweep_idx; g_sweep_win = sweep_win;
+}
 // One CTA of the product kernel over a multi-problem batch laid out like fq_solve_multi (include/faster_b200.h); plan tables
 // TZ / T0 / FT from fq_plan_tables.  Returns 0, -1 for an (N, mode) the harness does not instantiate, -2 if the batch needs more
 // shared memory than a CTA has.
@@ -128,6 +144,13 @@ int emu_solve_multi(int N, int force_final, const double* TZ, const double* T0, 
   c.a.feasible = feasible; c.a.cost = cost; c.a.coeffs = coeffs; c.a.iters = iters; c.a.row_tol = row_tol;
   std::vector<int> counters((size_t)n_prob + 1, 0);
   c.counters = counters.data();
+  std::vector<unsigned long long> first((size_t)n_prob, ~0ull);
+  if (g_early_exit) { c.a.first_feasible = first.data(); c.a.sorted_dt = 1; c.a.ee_width = g_sweep_n_sigma; }
+  if (g_sweep_n_sigma > 0 && n_prob == 1 && coeffs)
+  {
+    c.a.sweep_done = counters.data() + n_prob; c.a.sweep_n_sigma = g_sweep_n_sigma; c.a.sweep_idx = g_sweep_idx; c.a.sweep_win = g_sweep_win;
+  }
+  g_early_exit = 0; g_sweep_n_sigma = 0;
   const int key = N * 2 + (force_final ? 1 : 0);
   switch (key)
   {

@@ -35,6 +35,8 @@ def _emu(defines=()):
     L = C.CDLL(out)
     L.emu_solve_multi.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + \
                                  [C.c_void_p] * 3 + [C.c_double] + [C.c_void_p] * 4
+    L.emu_set_sweep.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.emu_set_sweep.restype = None
     _libs[key] = L
     return L
 
@@ -158,3 +160,47 @@ def test_guards_of_the_kernel(oracle, demo_corridor):
     # a per-polytope hint that makes the item list too short for this assignment
     got = solve_multi(_emu(), N, True, [fx["x0"]], [fx["xf"]], [fx["lim"]], [0, 3], fo, Ab, [0, 2], [0.8, 1.0], sig[:2], max_poly_faces=2)
     assert not got[0].any() and (got[3] == -2).all()
+
+
+def test_sweep_selection_and_early_exit_inside_the_kernel(oracle, demo_corridor):
+    """The drop-in class's sweep (fq_gen_new_traj): candidates dt-major, the warp that finishes the LAST candidate selects
+    genNewTraj's winner inside the kernel -- first time allocation with a feasible assignment, then minimum cost, then lowest
+    index (solverGurobi.cpp:445-472) -- and writes the record a host-mapped buffer receives on the GPU.  With the early exit
+    (first feasible factor wins) candidates beyond the winning time allocation are skipped (iters = -3) and the winner, its cost
+    and its coefficients are the same."""
+    fx = demo_corridor
+    N = fx["N"]
+    sig = cr.monotone_sigmas(N, 3)
+    facs = np.array([0.3, 0.5, 0.6, 0.8, 1.0, 1.5, 2.0])
+    dts, sigs = np.repeat(facs, len(sig)), np.tile(sig, (len(facs), 1))
+    fo = np.concatenate([[0], np.cumsum([len(b) for _, b in fx["polys"]])])
+    Ab = np.vstack([np.hstack([A, np.asarray(b)[:, None]]) for A, b in fx["polys"]])
+    f, c, co = oracle.solve_batch(N, fx["x0"], fx["xf"], fx["lim"], fx["polys"], dts, sigs, True, True, threads=4)
+    F = f.reshape(len(facs), len(sig)).astype(bool)
+    dt_win = int(np.flatnonzero(F.any(axis=1))[0])
+    cw = np.where(F[dt_win], c.reshape(len(facs), -1)[dt_win], np.inf)
+    sig_win = int(np.argmin(cw))
+    assert 0 < dt_win < len(facs) - 1                             # infeasible factors before the winner, feasible ones after it
+    L = _emu()
+    rec = {}
+    for ee in (0, 1):
+        idx, win = np.full(2, -7, np.int32), np.zeros(1 + 12 * N)
+        L.emu_set_sweep(ee, len(sig), idx.ctypes.data, win.ctypes.data)
+        got = solve_multi(L, N, True, [fx["x0"]], [fx["xf"]], [fx["lim"]], [0, 3], fo, Ab, [0, len(dts)], dts, sigs)
+        assert list(idx) == [dt_win, sig_win], (ee, idx)
+        k = dt_win * len(sig) + sig_win
+        assert abs(win[0] - c[k]) <= 1e-9 * c[k] and np.abs(win[1:] - co[k].reshape(-1)).max() <= 1e-7
+        upto = (dt_win + 1) * len(sig)
+        assert np.array_equal(got[0][:upto], f[:upto])            # everything at or below the winning time allocation is solved
+        rec[ee] = (win.copy(), got)
+    assert rec[0][0].tobytes() == rec[1][0].tobytes()             # same winner record, bit for bit
+    full, early = rec[0][1], rec[1][1]
+    assert np.array_equal(full[0], f) and (full[3] != -3).all()
+    skipped = early[3] == -3
+    assert skipped.any() and not skipped[:upto].any() and not early[0][skipped].any()
+    # no feasible candidate at all: the record says so
+    idx, win = np.full(2, -7, np.int32), np.zeros(1 + 12 * N)
+    L.emu_set_sweep(0, len(sig), idx.ctypes.data, win.ctypes.data)
+    n2 = 2 * len(sig)
+    got = solve_multi(L, N, True, [fx["x0"]], [fx["xf"]], [fx["lim"]], [0, 3], fo, Ab, [0, n2], dts[:n2] * 0.2, sigs[:n2])
+    assert not got[0].any() and list(idx) == [-1, -1] and np.isinf(win[0])
