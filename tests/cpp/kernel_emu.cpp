@@ -17,77 +17,6 @@ namespace fqt
 alignas(16) unsigned char smem_raw[232 * 1024];
 }
 
-namespace simt
-{
-Block* g = nullptr;
-
-static void trampoline()
-{
-  Block* b = g;
-  b->entry(b->arg);
-  self().wait = DONE;
-  swapcontext(&self().ctx, &b->sched);
-}
-
-void run_block(dim3 grid, dim3 block, uint3 bidx, void (*entry)(void*), void* arg, size_t stack_bytes)
-{
-  Block b;
-  b.grid = grid; b.block = block; b.bidx = bidx; b.entry = entry; b.arg = arg;
-  const int n = (int)block.x;
-  b.f.resize((size_t)n);
-  g = &b;
-  for (int i = 0; i < n; i++)
-  {
-    Fiber& f = b.f[(size_t)i];
-    f.tid = (unsigned)i;
-    f.stack.resize(stack_bytes);
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = f.stack.data();
-    f.ctx.uc_stack.ss_size = f.stack.size();
-    f.ctx.uc_link = &b.sched;
-    makecontext(&f.ctx, trampoline, 0);
-  }
-  for (;;)
-  {
-    bool ran = false, all_done = true;
-    for (int i = 0; i < n; i++)
-    {
-      if (b.f[(size_t)i].wait != NONE) continue;
-      b.cur = i;
-      swapcontext(&b.sched, &b.f[(size_t)i].ctx);
-      ran = true;
-    }
-    // a warp whose live lanes all wait on a collective goes on
-    for (int w = 0; w < n; w += 32)
-    {
-      int waiting = 0, live = 0;
-      for (int l = w; l < w + 32 && l < n; l++) { live += b.f[(size_t)l].wait != DONE; waiting += b.f[(size_t)l].wait == WARP; }
-      if (live && waiting == live)
-        for (int l = w; l < w + 32 && l < n; l++) if (b.f[(size_t)l].wait == WARP) b.f[(size_t)l].wait = NONE;
-    }
-    int at_barrier = 0, live = 0, any = 0;
-    for (int i = 0; i < n; i++)
-    {
-      const int wt = b.f[(size_t)i].wait;
-      live += wt != DONE; at_barrier += wt == BLOCK; all_done = all_done && wt == DONE;
-      if (wt == BLOCK) any |= b.f[(size_t)i].pred;
-    }
-    if (live && at_barrier == live)
-    {
-      b.block_or = any;
-      for (int i = 0; i < n; i++) if (b.f[(size_t)i].wait == BLOCK) { b.f[(size_t)i].wait = NONE; b.f[(size_t)i].pred = 0; }
-    }
-    if (all_done) break;
-    if (!ran)
-    { // nobody could run and nothing was released in the previous round: a deadlock in the emulated code
-      bool released = false;
-      for (int i = 0; i < n; i++) released = released || b.f[(size_t)i].wait == NONE;
-      if (!released) { std::fprintf(stderr, "simt_emu: deadlock (divergent collective?)\n"); std::abort(); }
-    }
-  }
-  g = nullptr;
-}
-}  // namespace simt
 
 namespace
 {

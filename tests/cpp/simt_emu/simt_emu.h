@@ -17,8 +17,11 @@
 #define __global__
 #define __device__
 #define __host__
+#ifndef __shared__
 #define __shared__            /* the dynamic shared array is one static buffer of the harness; the kernel's one static
-                                 __shared__ variable belongs to a build mode (FQ_WARP_ADOPT = 0) the harness does not compile */
+                                 __shared__ variable belongs to a build mode (FQ_WARP_ADOPT = 0) the harness does not compile.
+                                 A translation unit whose kernels use static __shared__ variables defines it as `static`. */
+#endif
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
@@ -54,7 +57,7 @@ struct Block
   void (*entry)(void*) = nullptr;
   void* arg = nullptr;
 };
-extern Block* g;
+inline Block* g = nullptr;
 inline Fiber& self() { return g->f[(size_t)g->cur]; }
 inline void yield(int kind)
 {
@@ -75,7 +78,6 @@ inline int warp_arrive(unsigned long long bits)
 inline unsigned long long lane_val(int lane, int ph) { return g->f[(size_t)((g->cur & ~31) + (lane & 31))].val[ph]; }
 inline int my_lane() { return g->cur & 31; }
 
-void run_block(dim3 grid, dim3 block, uint3 bidx, void (*entry)(void*), void* arg, size_t stack_bytes = 512 * 1024);
 }  // namespace simt
 
 struct SimtIdx { unsigned x, y, z; };
@@ -168,4 +170,78 @@ using std::fmin;
 inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
 inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; if (v < o) *p = v; return o; }
+inline int atomicMin(int* p, int v) { const int o = *p; if (v < o) *p = v; return o; }
+using std::isfinite;
 inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long c, unsigned long long v) { const unsigned long long o = *p; if (o == c) *p = v; return o; }
+
+// ---- the scheduler: runs every fibre until it waits, releases warps / the block when all their live members have arrived
+#include <cstdio>
+namespace simt
+{
+inline void trampoline()
+{
+  Block* b = g;
+  b->entry(b->arg);
+  self().wait = DONE;
+  swapcontext(&self().ctx, &b->sched);
+}
+
+inline void run_block(dim3 grid, dim3 block, uint3 bidx, void (*entry)(void*), void* arg, size_t stack_bytes = 512 * 1024)
+{
+  Block b;
+  b.grid = grid; b.block = block; b.bidx = bidx; b.entry = entry; b.arg = arg;
+  const int n = (int)block.x;
+  b.f.resize((size_t)n);
+  g = &b;
+  for (int i = 0; i < n; i++)
+  {
+    Fiber& f = b.f[(size_t)i];
+    f.tid = (unsigned)i;
+    f.stack.resize(stack_bytes);
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack.data();
+    f.ctx.uc_stack.ss_size = f.stack.size();
+    f.ctx.uc_link = &b.sched;
+    makecontext(&f.ctx, trampoline, 0);
+  }
+  for (;;)
+  {
+    bool ran = false, all_done = true;
+    for (int i = 0; i < n; i++)
+    {
+      if (b.f[(size_t)i].wait != NONE) continue;
+      b.cur = i;
+      swapcontext(&b.sched, &b.f[(size_t)i].ctx);
+      ran = true;
+    }
+    // a warp whose live lanes all wait on a collective goes on
+    for (int w = 0; w < n; w += 32)
+    {
+      int waiting = 0, live = 0;
+      for (int l = w; l < w + 32 && l < n; l++) { live += b.f[(size_t)l].wait != DONE; waiting += b.f[(size_t)l].wait == WARP; }
+      if (live && waiting == live)
+        for (int l = w; l < w + 32 && l < n; l++) if (b.f[(size_t)l].wait == WARP) b.f[(size_t)l].wait = NONE;
+    }
+    int at_barrier = 0, live = 0, any = 0;
+    for (int i = 0; i < n; i++)
+    {
+      const int wt = b.f[(size_t)i].wait;
+      live += wt != DONE; at_barrier += wt == BLOCK; all_done = all_done && wt == DONE;
+      if (wt == BLOCK) any |= b.f[(size_t)i].pred;
+    }
+    if (live && at_barrier == live)
+    {
+      b.block_or = any;
+      for (int i = 0; i < n; i++) if (b.f[(size_t)i].wait == BLOCK) { b.f[(size_t)i].wait = NONE; b.f[(size_t)i].pred = 0; }
+    }
+    if (all_done) break;
+    if (!ran)
+    { // nobody could run and nothing was released in the previous round: a deadlock in the emulated code
+      bool released = false;
+      for (int i = 0; i < n; i++) released = released || b.f[(size_t)i].wait == NONE;
+      if (!released) { std::fprintf(stderr, "simt_emu: deadlock (divergent collective?)\n"); std::abort(); }
+    }
+  }
+  g = nullptr;
+}
+}  // namespace simt

@@ -204,3 +204,95 @@ def test_sweep_selection_and_early_exit_inside_the_kernel(oracle, demo_corridor)
     n2 = 2 * len(sig)
     got = solve_multi(L, N, True, [fx["x0"]], [fx["xf"]], [fx["lim"]], [0, 3], fo, Ab, [0, n2], dts[:n2] * 0.2, sigs[:n2])
     assert not got[0].any() and list(idx) == [-1, -1] and np.isinf(win[0])
+
+
+# ---- the chained replan: every kernel of fq_replan_pairs_dev's submission (faster_b200/csrc/fq_pair_capi.cu:93-141) under emulation
+_PAIR = None
+RESULT_DT = np.dtype([("whole_dt_index", np.int32), ("whole_sigma_index", np.int32), ("safe_dt_index", np.int32), ("safe_sigma_index", np.int32),
+                      ("whole_cost", np.float64), ("safe_cost", np.float64), ("whole_dt", np.float64), ("safe_dt", np.float64),
+                      ("whole_dt_base", np.float64), ("safe_dt_base", np.float64), ("n_samples_whole", np.int32), ("k_safe", np.int32),
+                      ("R", np.float64, (9,))])
+
+
+def _pair_lib():
+    global _PAIR
+    if _PAIR is None:
+        out = os.path.join(ROOT, "tests", "cpp", "_build", "libpair_emu.so")
+        srcs = [os.path.join(ROOT, "tests", "cpp", "pair_emu.cpp"), os.path.join(ROOT, "tests", "cpp", "simt_emu", "simt_emu.h"),
+                os.path.join(ROOT, "faster_b200", "csrc", "fq_pair.cuh"), os.path.join(ROOT, "faster_b200", "csrc", "fq_dtinit.h")]
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I", os.path.join(ROOT, "tests", "cpp"),
+                                   "-I", os.path.join(ROOT, "tests", "cpp", "simt_emu"), "-I", os.path.join(ROOT, "faster_b200", "csrc"),
+                                   "-I", os.path.join(ROOT, "include"), srcs[0], "-o", out])
+        _PAIR = C.CDLL(out)
+        for name in ("emu_dtbase", "emu_expand_grid", "emu_select_multi", "emu_pair_mid", "emu_pair_final"):
+            getattr(_PAIR, name).restype = None
+    return _PAIR
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def emulated_replan_pairs(w):
+    """fq_replan_pairs_dev's submission, kernel by kernel, through the emulation: dt base -> grid -> whole sweep -> selection ->
+    winners' coefficients -> R -> dt base (safe) -> grid -> safe sweep -> selection -> result records."""
+    P, Nw, Ns, DC = w["n_prob"], w["N_whole"], w["N_safe"], w["DC"]
+    K, L = _pair_lib(), _emu()
+    c = lambda a, t: np.ascontiguousarray(a, t)
+    x0, xfw, xfs, lim = c(w["x0"], np.float64), c(w["xf_whole"], np.float64), c(w["xf_safe"], np.float64), c(w["lim"], np.float64)
+    out = {}
+    st = {}
+    for kind, N, ff, xs, xf in (("whole", Nw, True, x0, xfw), ("safe", Ns, False, None, xfs)):
+        fac, sg = c(w["factors_" + kind], np.float64), c(w["sigmas_" + kind], np.uint8)
+        nf, ns = len(fac), len(sg)
+        n = P * nf * ns
+        if kind == "safe":
+            xs = st["x0_safe"]
+        base = np.zeros(P)
+        K.emu_dtbase(P, N, C.c_double(DC), _p(xs), _p(xf), _p(lim), _p(base))
+        dt, sig, co = np.zeros(n), np.zeros((n, N), np.uint8), np.zeros(P + 1, np.int32)
+        K.emu_expand_grid(P, N, nf, ns, _p(fac), _p(sg), _p(base), _p(dt), _p(sig), _p(co))
+        feas, cost, _, _ = solve_multi(L, N, ff, np.where(np.isfinite(xs), xs, np.nan), xf, lim, w["poly_ofs_" + kind], w["face_ofs_" + kind],
+                                       w["Ab_" + kind], co, dt, sig, max_faces=w["max_faces_" + kind], max_poly_faces=w["max_poly_faces_" + kind])
+        wi, wc, wdt, ws, wo = np.zeros(P, np.int32), np.zeros(P), np.zeros(P), np.zeros((P, N), np.uint8), np.zeros(P + 1, np.int32)
+        K.emu_select_multi(P, N, ns, _p(co), _p(dt), _p(sig), _p(feas), _p(cost), _p(wi), _p(wc), _p(wdt), _p(ws), _p(wo))
+        # winners' coefficients: one candidate per corridor through the same solve kernel (losers: dt = NaN -> not solved)
+        _, _, coeffs, _ = solve_multi(L, N, ff, np.where(np.isfinite(xs), xs, np.nan), xf, lim, w["poly_ofs_" + kind], w["face_ofs_" + kind],
+                                      w["Ab_" + kind], wo, wdt, ws, max_faces=w["max_faces_" + kind], max_poly_faces=w["max_poly_faces_" + kind])
+        st[kind] = dict(base=base, wi=wi, wc=wc, wdt=wdt, ns=ns)
+        out["feasible_" + kind], out["cost_" + kind], out["coeffs_" + kind] = feas, cost, coeffs
+        if kind == "whole":
+            x0s, nsamp, ksafe = np.zeros((P, 9)), np.zeros(P, np.int32), np.zeros(P, np.int32)
+            K.emu_pair_mid(P, N, C.c_double(DC), C.c_double(w["r_fraction"]), _p(c(coeffs, np.float64)), _p(wdt), _p(wi), _p(x0s), _p(nsamp), _p(ksafe))
+            st["x0_safe"], st["nsamp"], st["ksafe"] = x0s, nsamp, ksafe
+    res = np.zeros(P, RESULT_DT)
+    assert RESULT_DT.itemsize == 144
+    a, b = st["whole"], st["safe"]
+    K.emu_pair_final(P, a["ns"], b["ns"], _p(a["wi"]), _p(b["wi"]), _p(st["nsamp"]), _p(st["ksafe"]), _p(a["wc"]), _p(b["wc"]), _p(a["wdt"]),
+                     _p(b["wdt"]), _p(a["base"]), _p(b["base"]), _p(st["x0_safe"]), _p(res))
+    out["results"] = res
+    return out
+
+
+def test_chained_replan_through_the_emulated_kernels(oracle):
+    """The bench's hot path end to end without a GPU: corridors of the committed config-4 forest fixture through every kernel of
+    the chain, against the CPU chain (oracle/fq_cpu_port.c's fqc_replan_pairs): the same time-allocation bases bit for bit, the
+    same flags for all 2 x 1024 candidates per corridor, the same winners, R to rounding, costs to 1e-9."""
+    import bench
+    w = bench.load_cfg4(0, 3)
+    got = emulated_replan_pairs(w)
+    ref = oracle.replan_pairs_port(w, threads=4)
+    r, q = got["results"], ref["results"]
+    assert np.array_equal(r["whole_dt_base"], q["whole_dt_base"]) and np.array_equal(r["safe_dt_base"], q["safe_dt_base"])
+    for k in ("whole", "safe"):
+        assert np.array_equal(got["feasible_" + k], ref["feasible_" + k]), k
+        ok = ref["feasible_" + k].astype(bool)
+        assert (np.abs(got["cost_" + k][ok] - ref["cost_" + k][ok]) / np.abs(ref["cost_" + k][ok])).max() <= 1e-9
+    for f in ("whole_dt_index", "whole_sigma_index", "safe_dt_index", "safe_sigma_index", "n_samples_whole", "k_safe"):
+        assert np.array_equal(r[f], q[f]), f
+    assert (r["whole_dt_index"] >= 0).all() and (r["safe_dt_index"] >= 0).any()
+    assert np.abs(r["R"] - q["R"]).max() <= 1e-9 and np.allclose(r["whole_cost"], q["whole_cost"], rtol=1e-9) and \
+        np.allclose(r["safe_cost"], q["safe_cost"], rtol=1e-9, equal_nan=True)
+    assert np.abs(got["coeffs_whole"] - ref["coeffs_whole"]).max() <= 1e-7
